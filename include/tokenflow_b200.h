@@ -1,0 +1,98 @@
+/* tokenflow_b200 — C ABI of the B200-native TokenFlow hot path.
+ *
+ * The reference (omerbt/TokenFlow @ 5dd6a69) is pure Python and has no FFI layer; its boundary for
+ * this path is the hook surface of tokenflow_utils.py.  This library is what a replacement for those
+ * hooks binds (ctypes stub shown in INTEGRATION.md; `tokenflow_b200/ops.py` is that stub in
+ * product form).  Every entry point cites the reference lines whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - plain C: raw device pointers, explicit shapes/strides, an opaque CUDA stream handle
+ *     (`cudaStream_t`; pass `torch.cuda.current_stream().cuda_stream`).  No torch types.
+ *   - every function returns an int status: 0 = ok, nonzero = error (tf_last_error() explains).
+ *     Nothing throws, nothing allocates device memory, nothing synchronises the device: work is
+ *     enqueued on `stream` and the caller owns every buffer.
+ *   - "host" pointers are read synchronously during the call (small per-frame tables passed to the
+ *     kernels by value); "device" pointers must be valid on the current device.
+ *   - fp16 activations, int32 indices.  dim and head_dim must be multiples of 8; device pointers
+ *     16-byte aligned; tensors contiguous unless a stride argument says otherwise.
+ *   - compiled for sm_100a only; the kernels use tcgen05 / TMEM / TMA.
+ */
+#ifndef TOKENFLOW_B200_H_
+#define TOKENFLOW_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* tf_stream_t; /* cudaStream_t */
+
+#define TF_MAX_FRAMES 64        /* frames per tf_nn_field / tf_propagate call        */
+#define TF_MAX_ATTN_SAMPLES 160 /* output samples (stream, keyframe) per attention call */
+
+/* Library ABI version (major*1000 + minor). */
+int tf_version(void);
+/* Thread-local description of the last error returned on this thread ("" if none). */
+const char* tf_last_error(void);
+/* Number of kernel launches enqueued by this library since load (all threads); bench.py reports
+ * the per-step difference as `gpu_launches`. */
+int64_t tf_launch_count(void);
+
+/* Row L2-normalisation feeding the NN field:  out[r,:] = fp16(x[r,:] / ||x[r,:]||_2).
+ * Replaces util.py:66-67 (`x / x.norm(dim=-1, keepdim=True)`, fp32 under autocast) plus the fp16
+ * operand cast autocast applies to the following matmul (util.py:68).
+ *   x            device, [rows, dim] fp32 (x_is_f32 != 0) or fp16, row pitch `x_row_stride` elements
+ *   out_f16      device, [rows, dim] fp16, contiguous */
+int tf_unit_rows(const void* x, int x_is_f32, int64_t rows, int dim, int64_t x_row_stride, void* out_f16,
+                 tf_stream_t stream);
+
+/* Token nearest-neighbour field.  Replaces tokenflow_utils.py:329-348 (+ util.py:68 `x @ y.T`,
+ * fp16 output under autocast, and the two argmax reductions :340-343):
+ *   idx_a[f,p] = argmax_c fp16( x_unit[f,p,:] . piv_unit[kf_a[f],c,:] )     first index on ties
+ *   idx_b[f,p] = same against keyframe kf_b[f]            (skipped for frames with kf_b[f] < 0)
+ *   x_unit    device [F, S, dim] fp16 unit rows (tf_unit_rows of the source-stream norm1 output)
+ *   piv_unit  device [K, S, dim] fp16 unit rows of the cached source-stream pivot features
+ *   kf_a,kf_b host   [F] keyframe ids in [0,K); reference batch i: kf_a = i, kf_b = i-1 (or -1)
+ *   idx_a,idx_b device [F, S] int32 (idx_b may be NULL when no frame has a second keyframe) */
+int tf_nn_field(const void* x_unit, const void* piv_unit, const int32_t* kf_a, const int32_t* kf_b, int F, int S,
+                int dim, int K, int32_t* idx_a, int32_t* idx_b, tf_stream_t stream);
+
+/* NN-indexed feature propagation.  Replaces tokenflow_utils.py:361-397 (keyframe slice, two
+ * gathers, blend weights, blend, residual add):
+ *   out[s,f,p,:] = w[f]*A[s,kf_a[f],idx_a[f,p],:] + (1-w[f])*A[s,kf_b[f],idx_b[f,p],:] (+ residual[s,f,p,:])
+ *   (kf_b[f] < 0:  out = A[s,kf_a[f],idx_a[f,p],:] (+ residual))
+ *   A         device [3, K, S, dim] fp16   (cached attn1 output of the pivotal pass, `kf_attn_output`)
+ *   w         host   [F] fp32 blend weights (reference: sigmoid(d2/(d1+d2)), :375-383)
+ *   residual  device [3, F, S, dim] fp16 or NULL  (the block's `hidden_states`, :396-397)
+ *   out       device [3, F, S, dim] fp16 (out_is_f32 == 0) or fp32 (the reference's promoted dtype) */
+int tf_propagate(const void* A, const int32_t* idx_a, const int32_t* idx_b, const int32_t* kf_a,
+                 const int32_t* kf_b, const float* w, int F, int S, int dim, int K, const void* residual,
+                 void* out, int out_is_f32, tf_stream_t stream);
+
+/* Extended attention of one pivotal pass.  Replaces the body of the attn1 closure between the
+ * q/k/v projections and `to_out` (tokenflow_utils.py:124-197 PnP flavour, :234-279 SDEdit flavour).
+ *   q,k,v   device [3n, S, heads, d] fp16; consecutive tokens `tok_stride` elements apart (heads*d
+ *           when contiguous, 3*heads*d for a fused qkv buffer); samples S*tok_stride apart
+ *   out     device [3n, S, heads*d] fp16 contiguous
+ *   inject  != 0: PnP q/k injection — uncond and cond samples read the source stream's q and k
+ *           (reference :124-130) by aliasing, nothing is copied
+ * Batch axis is [source | uncond | cond] thirds like the reference (:117).  Source samples attend
+ * to their own frame, uncond/cond samples to all n frames of their stream. */
+int tf_ext_attn_fwd(const void* q, const void* k, const void* v, int64_t tok_stride, int n_frames, int S,
+                    int heads, int d, float scale, int inject, void* out, tf_stream_t stream);
+
+/* General form used when the pivotal pass is sharded across GPUs: `n_out` output samples, each
+ * described by host arrays (all length n_out): which slab of `out` it writes, which slab of q it
+ * reads, the first k / v slab it attends to and how many consecutive slabs (1 = own frame, n = all
+ * keyframes).  q has q_slabs slabs of [S, heads, d]; k and v have kv_slabs. */
+int tf_ext_attn_fwd_table(const void* q, int q_slabs, int64_t q_tok_stride, const void* k, const void* v,
+                          int kv_slabs, int64_t kv_tok_stride, int n_out, const int32_t* out_slab,
+                          const int32_t* q_slab, const int32_t* k_slab0, const int32_t* v_slab0,
+                          const int32_t* n_kv, int S, int heads, int d, float scale, void* out,
+                          tf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOKENFLOW_B200_H_ */
