@@ -1,0 +1,148 @@
+"""The caller of the hot path: the denoising loop of the reference drivers
+(run_tokenflow_pnp.py:195-240, 264-273; run_tokenflow_sdedit.py:154-205), without the parts that
+need Stable-Diffusion weights (VAE, CLIP, image/video I/O — out of scope).
+
+`TokenFlowEditor` is parameterised by the hook module, so the same loop runs
+  * this package's hooks (`tokenflow_b200.tokenflow_utils`, CUDA kernels) — the product,
+  * the unmodified reference hooks (via oracle/ref_shim.py) — golden-vector generation,
+  * this package's hooks with oracle ops installed — CPU plumbing tests / CPU baseline.
+
+Per denoising step (reference batched_denoise_step, :220-233):
+  1. draw one random keyframe per batch of B frames (CPU generator, like the reference);
+  2. pivotal pass: UNet over [source | uncond | cond] x K keyframes, output discarded — it only
+     fills the per-block caches (pivot features, extended-attention outputs);
+  3. frame passes: UNet over each batch of B frames; self-attention is replaced by NN propagation;
+  4. classifier-free guidance + DDIM update per batch.
+"""
+from __future__ import annotations
+
+import contextlib
+import os
+from typing import Callable, Dict, Optional
+
+import torch
+import torch.nn as nn
+
+
+class TokenFlowEditor(nn.Module):
+    def __init__(self, unet: nn.Module, scheduler, hooks, config: Dict, text_embeds: torch.Tensor,
+                 pnp_guidance_embeds: torch.Tensor, source_latents: Optional[Callable[[int], torch.Tensor]] = None):
+        """config keys (names follow configs/config_pnp.yaml): n_frames, batch_size, n_timesteps,
+        guidance_scale, mode ('pnp' | 'sdedit'), pnp_attn_t, pnp_f_t, start (sdedit), latents_path.
+        text_embeds: [2, L, C] (uncond, cond);  pnp_guidance_embeds: [1, L, C] (inversion prompt)."""
+        super().__init__()
+        self.unet = unet
+        self.scheduler = scheduler
+        self.hooks = hooks
+        self.config = dict(config)
+        self.text_embeds = text_embeds
+        self.pnp_guidance_embeds = pnp_guidance_embeds
+        self.latents_path = self.config.get("latents_path")
+        self._source_latents = source_latents
+        self.device = next(unet.parameters()).device
+        self.scheduler.set_timesteps(self.config["n_timesteps"], device=self.device)
+        if self.config.get("mode", "pnp") == "sdedit":        # run_tokenflow_sdedit.py:57
+            start = float(self.config.get("start", 0.9))
+            self.scheduler.timesteps = self.scheduler.timesteps[int(1 - start * self.config["n_timesteps"]):]
+        self.keyframe_log = []
+
+    # ------------------------------------------------------------------------------------
+    def init_method(self):
+        """run_tokenflow_pnp.py:235-240 / run_tokenflow_sdedit.py:191-193."""
+        h = self.hooks
+        if self.config.get("mode", "pnp") == "pnp":
+            n = self.config["n_timesteps"]
+            qk_t = int(n * self.config.get("pnp_attn_t", 0.5))
+            conv_t = int(n * self.config.get("pnp_f_t", 0.8))
+            self.qk_injection_timesteps = self.scheduler.timesteps[:qk_t] if qk_t >= 0 else []
+            self.conv_injection_timesteps = self.scheduler.timesteps[:conv_t] if conv_t >= 0 else []
+            h.register_extended_attention_pnp(self, self.qk_injection_timesteps)
+            h.register_conv_injection(self, self.conv_injection_timesteps)
+        else:
+            h.register_extended_attention(self)
+        h.set_tokenflow(self.unet)
+
+    def source_latents_t(self, t: int) -> torch.Tensor:
+        if self._source_latents is not None:
+            return self._source_latents(t)
+        return self.hooks.load_source_latents_t(t, self.latents_path)
+
+    # ------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def denoise_step(self, x, t, indices):
+        """run_tokenflow_pnp.py:195-218."""
+        source_latents = self.source_latents_t(int(t))[indices].to(x.device, x.dtype)
+        latent_model_input = torch.cat([source_latents] + ([x] * 2))
+        self.hooks.register_time(self, int(t))
+        text_embed_input = torch.cat([self.pnp_guidance_embeds.repeat(len(indices), 1, 1),
+                                      torch.repeat_interleave(self.text_embeds, len(indices), dim=0)])
+        noise_pred = self.unet(latent_model_input, t, encoder_hidden_states=text_embed_input)['sample']
+        _, noise_pred_uncond, noise_pred_cond = noise_pred.chunk(3)
+        noise_pred = noise_pred_uncond + self.config["guidance_scale"] * (noise_pred_cond - noise_pred_uncond)
+        return self.scheduler.step(noise_pred, t, x)['prev_sample']
+
+    def _autocast(self):
+        if self.device.type == "cuda" and self.config.get("autocast", True):
+            return torch.autocast(device_type="cuda", dtype=torch.float16)    # run_tokenflow_pnp.py:220
+        return contextlib.nullcontext()
+
+    def draw_keyframes(self, n: int) -> torch.Tensor:
+        """run_tokenflow_pnp.py:224 — one uniformly random frame inside every batch (CPU RNG)."""
+        batch_size = self.config["batch_size"]
+        return torch.randint(batch_size, (n // batch_size,)) + torch.arange(0, n, batch_size)
+
+    def batched_denoise_step(self, x, t, indices):
+        """run_tokenflow_pnp.py:220-233."""
+        h = self.hooks
+        batch_size = self.config["batch_size"]
+        with self._autocast():
+            pivotal_idx = self.draw_keyframes(len(x))
+            self.keyframe_log.append(pivotal_idx.tolist())
+            h.register_pivotal(self, True)
+            self.denoise_step(x[pivotal_idx], t, indices[pivotal_idx])
+            h.register_pivotal(self, False)
+            denoised = []
+            for i, b in enumerate(range(0, len(x), batch_size)):
+                h.register_batch_idx(self, i)
+                denoised.append(self.denoise_step(x[b:b + batch_size], t, indices[b:b + batch_size]))
+            return torch.cat(denoised)
+
+    def sample_loop(self, x, indices=None, on_step: Optional[Callable] = None):
+        """run_tokenflow_pnp.py:264-273 without the VAE decode."""
+        if indices is None:
+            indices = torch.arange(len(x))
+        for i, t in enumerate(self.scheduler.timesteps):
+            x = self.batched_denoise_step(x, t, indices)
+            if on_step is not None:
+                on_step(i, int(t), x)
+        return x
+
+
+# --------------------------------------------------------------------------------------------
+# synthetic inputs: no SD weights / VAE / CLIP exist here
+# --------------------------------------------------------------------------------------------
+def synthetic_inputs(n_frames: int, latent_size: int, ctx_dim: int, n_timesteps: int, seed: int = 1,
+                     device="cpu", dtype=torch.float32, ctx_len: int = 77):
+    """x ~ N(0,1) [N,4,L,L]; one source latent tensor per sampling timestep; text embeddings
+    ~ N(0,1).  Deterministic in `seed` and independent of device."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n_frames, 4, latent_size, latent_size, generator=g)
+    text = torch.randn(2, ctx_len, ctx_dim, generator=g)
+    pnp = torch.randn(1, ctx_len, ctx_dim, generator=g)
+    ratio = 1000 // n_timesteps
+    timesteps = [(n_timesteps - 1 - i) * ratio + 1 for i in range(n_timesteps)]
+    src = {t: torch.randn(n_frames, 4, latent_size, latent_size, generator=g) for t in timesteps}
+    conv = lambda z: z.to(device=device, dtype=dtype)
+    return conv(x), conv(text), conv(pnp), {t: conv(v) for t, v in src.items()}
+
+
+def write_latents_dir(path: str, src: Dict[int, torch.Tensor], prompt: str = "synthetic") -> str:
+    """The preprocess -> edit hand-off format (preprocess.py:227-229, :313-314):
+    <path>/latents/noisy_latents_<t>.pt + <path>/inversion_prompt.txt."""
+    lat = os.path.join(path, "latents")
+    os.makedirs(lat, exist_ok=True)
+    for t, v in src.items():
+        torch.save(v, os.path.join(lat, f"noisy_latents_{t}.pt"))
+    with open(os.path.join(path, "inversion_prompt.txt"), "w") as f:
+        f.write(prompt)
+    return lat

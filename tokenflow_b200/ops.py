@@ -1,0 +1,211 @@
+"""ctypes binding of libtokenflow_b200.so (include/tokenflow_b200.h) and the op layer the hooks call.
+
+`CudaOps` is the product and the only op implementation in this package: every method enqueues a
+hand-written sm_100a kernel on the current CUDA stream through the C ABI.  There is no CPU or
+PyTorch fallback — constructing `CudaOps` without the built library or without a CUDA device
+raises, loudly.  (Tests substitute an oracle-backed op object through
+`tokenflow_utils._install_ops_for_testing`; that object lives under `oracle/`, not here.)
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+from pathlib import Path
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+LIB_NAME = "libtokenflow_b200.so"
+TF_MAX_FRAMES = 64
+TF_MAX_ATTN_SAMPLES = 160
+
+_c_i32p = ctypes.POINTER(ctypes.c_int32)
+_c_f32p = ctypes.POINTER(ctypes.c_float)
+
+# name -> (restype, argtypes); mirrors include/tokenflow_b200.h one to one
+_SIGNATURES = {
+    "tf_version": (ctypes.c_int, []),
+    "tf_last_error": (ctypes.c_char_p, []),
+    "tf_launch_count": (ctypes.c_int64, []),
+    "tf_unit_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int64,
+                                    ctypes.c_void_p, ctypes.c_void_p]),
+    "tf_nn_field": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _c_i32p, _c_i32p, ctypes.c_int, ctypes.c_int,
+                                   ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "tf_propagate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _c_i32p, _c_i32p, _c_f32p,
+                                    ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                    ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "tf_ext_attn_fwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                       ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "tf_ext_attn_fwd_table": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int, _c_i32p,
+                                             _c_i32p, _c_i32p, _c_i32p, _c_i32p, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
+}
+
+
+class TokenflowB200Error(RuntimeError):
+    pass
+
+
+def library_path() -> Path:
+    return Path(__file__).resolve().parent / LIB_NAME
+
+
+_LIB = None
+
+
+def load_library() -> ctypes.CDLL:
+    """dlopen the in-tree library and declare every prototype.  Needs no GPU."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not path.exists():
+        raise TokenflowB200Error(
+            f"{path} is missing: build it with `python -m tokenflow_b200._build` "
+            "(or __graft_entry__.build()).  tokenflow_b200 has no fallback path.")
+    lib = ctypes.CDLL(str(path))
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)           # AttributeError here = header and library disagree
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def exported_symbols() -> Sequence[str]:
+    return tuple(_SIGNATURES.keys())
+
+
+def blend_weights(n_frames: int) -> Sequence[float]:
+    """w[f] = sigmoid(d2/(d1+d2)), d1=|g-(iB+B//2)|, d2=|g-((i-1)B+B//2)|, g=iB+f (reference
+    tokenflow_utils.py:375-383); the batch index i cancels, so the table depends on B only.
+    Evaluated in fp32 with the same torch ops as the reference so the weights are bit-identical."""
+    f = torch.arange(0, n_frames)
+    d1 = torch.abs(f - n_frames // 2)
+    d2 = torch.abs(f + n_frames - n_frames // 2)
+    return torch.sigmoid(d2 / (d1 + d2)).tolist()
+
+
+def _i32(vals: Sequence[int]):
+    return (ctypes.c_int32 * len(vals))(*[int(v) for v in vals])
+
+
+def _f32(vals: Sequence[float]):
+    return (ctypes.c_float * len(vals))(*[float(v) for v in vals])
+
+
+class CudaOps:
+    """The hot-path operators, each one C-ABI call = one sm_100a kernel launch on the current stream."""
+
+    name = "cuda-sm100a"
+
+    def __init__(self):
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise TokenflowB200Error(
+                "tokenflow_b200 needs a CUDA device (sm_100a / B200); there is no CPU path.")
+        major, minor = torch.cuda.get_device_capability()
+        if major != 10:
+            raise TokenflowB200Error(f"tokenflow_b200 kernels are compiled for sm_100a only (got sm_{major}{minor})")
+
+    # -- helpers ---------------------------------------------------------------------------
+    def _check(self, status: int, what: str):
+        if status != 0:
+            msg = self.lib.tf_last_error().decode(errors="replace")
+            raise TokenflowB200Error(f"{what} failed (status {status}): {msg}")
+
+    @staticmethod
+    def _stream() -> int:
+        return torch.cuda.current_stream().cuda_stream
+
+    def launch_count(self) -> int:
+        return int(self.lib.tf_launch_count())
+
+    # -- operators -------------------------------------------------------------------------
+    def unit_rows(self, x: torch.Tensor) -> torch.Tensor:
+        """[..., dim] fp32/fp16 → fp16 unit rows (reference util.py:66-67 + autocast fp16 cast)."""
+        if x.dtype not in (torch.float32, torch.float16):
+            x = x.float()
+        dim = x.shape[-1]
+        x2 = x.reshape(-1, dim)
+        if x2.stride(-1) != 1:
+            x2 = x2.contiguous()
+        out = torch.empty(x2.shape, dtype=torch.float16, device=x.device)
+        self._check(self.lib.tf_unit_rows(x2.data_ptr(), int(x2.dtype == torch.float32), x2.shape[0], dim,
+                                          x2.stride(0), out.data_ptr(), self._stream()), "tf_unit_rows")
+        return out.view(*x.shape)
+
+    def nn_field(self, x_unit: torch.Tensor, piv_unit: torch.Tensor, kf_a: Sequence[int],
+                 kf_b: Sequence[int]) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        """x_unit [F,S,dim], piv_unit [K,S,dim] fp16 unit rows → int32 idx_a, idx_b [F,S]
+        (reference tokenflow_utils.py:335-343)."""
+        F_, S, dim = x_unit.shape
+        K = piv_unit.shape[0]
+        assert x_unit.dtype == torch.float16 and piv_unit.dtype == torch.float16
+        x_unit = x_unit.contiguous()
+        piv_unit = piv_unit.contiguous()
+        idx_a = torch.empty((F_, S), dtype=torch.int32, device=x_unit.device)
+        any_b = any(int(b) >= 0 for b in kf_b)
+        idx_b = torch.empty((F_, S), dtype=torch.int32, device=x_unit.device) if any_b else None
+        for f0 in range(0, F_, TF_MAX_FRAMES):
+            f1 = min(F_, f0 + TF_MAX_FRAMES)
+            self._check(self.lib.tf_nn_field(
+                x_unit[f0:f1].data_ptr(), piv_unit.data_ptr(), _i32(kf_a[f0:f1]), _i32(kf_b[f0:f1]), f1 - f0, S, dim,
+                K, idx_a[f0:f1].data_ptr(), idx_b[f0:f1].data_ptr() if idx_b is not None else None,
+                self._stream()), "tf_nn_field")
+        return idx_a, idx_b
+
+    def propagate(self, A: torch.Tensor, idx_a: torch.Tensor, idx_b: Optional[torch.Tensor],
+                  kf_a: Sequence[int], kf_b: Sequence[int], w: Sequence[float],
+                  residual: Optional[torch.Tensor], out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+        """A [3,K,S,dim] fp16; idx [F,S] int32; residual [3F,S,dim] fp16 or None → [3F,S,dim]
+        (reference tokenflow_utils.py:361-397)."""
+        three, K, S, dim = A.shape
+        out_dtype = torch.float16 if out_dtype is None else out_dtype
+        if A.dtype != torch.float16 or not A.is_contiguous():
+            A = A.to(torch.float16).contiguous()
+        assert three == 3
+        F_ = idx_a.shape[0]
+        if residual is not None:
+            residual = residual.to(torch.float16).contiguous().view(3, F_, S, dim)
+        out = torch.empty((3, F_, S, dim), dtype=out_dtype, device=A.device)
+        assert out_dtype in (torch.float16, torch.float32)
+        if F_ <= TF_MAX_FRAMES:
+            self._check(self.lib.tf_propagate(
+                A.data_ptr(), idx_a.data_ptr(), idx_b.data_ptr() if idx_b is not None else None, _i32(kf_a),
+                _i32(kf_b), _f32(w), F_, S, dim, K, residual.data_ptr() if residual is not None else None,
+                out.data_ptr(), int(out_dtype == torch.float32), self._stream()), "tf_propagate")
+        else:  # the [3,F,S,dim] layout is not sliceable along F without strides: chunk through temporaries
+            for f0 in range(0, F_, TF_MAX_FRAMES):
+                f1 = min(F_, f0 + TF_MAX_FRAMES)
+                res_c = residual[:, f0:f1].contiguous() if residual is not None else None
+                out_c = torch.empty((3, f1 - f0, S, dim), dtype=out_dtype, device=A.device)
+                self._check(self.lib.tf_propagate(
+                    A.data_ptr(), idx_a[f0:f1].data_ptr(), idx_b[f0:f1].data_ptr() if idx_b is not None else None,
+                    _i32(kf_a[f0:f1]), _i32(kf_b[f0:f1]), _f32(w[f0:f1]), f1 - f0, S, dim, K,
+                    res_c.data_ptr() if res_c is not None else None, out_c.data_ptr(),
+                    int(out_dtype == torch.float32), self._stream()), "tf_propagate")
+                out[:, f0:f1] = out_c
+        return out.view(3 * F_, S, dim)
+
+    def ext_attn(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: float,
+                 inject: bool) -> torch.Tensor:
+        """q,k,v [3n,S,dim] fp16 (same token stride) → [3n,S,dim] fp16, before to_out
+        (reference tokenflow_utils.py:124-197 / :234-279)."""
+        b, S, dim = q.shape
+        n = b // 3
+        d = dim // heads
+        q, k, v = (t if t.dtype == torch.float16 else t.to(torch.float16) for t in (q, k, v))
+        strides = {(t.stride(0), t.stride(1), t.stride(2)) for t in (q, k, v)}
+        tok = q.stride(1)
+        if len(strides) != 1 or q.stride(2) != 1 or q.stride(0) != S * tok:
+            q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+            tok = dim
+        out = torch.empty((b, S, dim), dtype=torch.float16, device=q.device)
+        self._check(self.lib.tf_ext_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), tok, n, S, heads, d,
+                                             float(scale), int(bool(inject)), out.data_ptr(), self._stream()),
+                    "tf_ext_attn_fwd")
+        return out

@@ -1,0 +1,340 @@
+"""Drop-in replacement for the reference's `tokenflow_utils.py` hook layer.
+
+Same public names, signatures and module-state contract as omerbt/TokenFlow's tokenflow_utils.py
+(consumed by `from tokenflow_utils import *` in run_tokenflow_pnp.py:16 / run_tokenflow_sdedit.py:15),
+so the reference drivers run unchanged — but the three hot operations underneath are hand-written
+sm_100a CUDA kernels reached through the C ABI in include/tokenflow_b200.h:
+
+    extended attention      attn1 closure        -> tf_ext_attn_fwd      (reference :114-199, :224-281)
+    NN field                TokenFlowBlock       -> tf_unit_rows + tf_nn_field   (:329-348, util.py:61-69)
+    propagation             TokenFlowBlock       -> tf_propagate         (:361-397)
+
+There is no PyTorch/CPU fallback: the first hot-path call constructs `ops.CudaOps`, which raises if
+the library or a B200 is missing.
+
+Differences from the reference that do not change results:
+  * per-pass host work is O(#blocks): module lists are discovered once per model instead of walking
+    `named_modules()` of UNet+VAE+CLIP on every register_* call (reference :8,:14);
+  * `t in injection_schedule` is a host-side set lookup, not a CUDA-tensor membership test with a
+    device sync per attn1 call (reference :124);
+  * PnP q/k injection (:124-130) copies nothing — the kernel reads the source stream's q/k;
+  * the frame pass can be driven per frame (`register_frame_table`) so frames, not only whole
+    batches, shard across GPUs; `register_batch_idx` keeps the reference meaning.
+"""
+from __future__ import annotations
+
+import os
+import weakref
+from typing import List, Optional, Sequence, Type
+
+import torch
+
+from .util import isinstance_str, batch_cosine_sim  # noqa: F401  (re-exported like the reference)
+
+__all__ = [
+    "register_pivotal", "register_batch_idx", "register_frame_table", "register_time", "load_source_latents_t",
+    "register_conv_injection", "register_extended_attention_pnp", "register_extended_attention",
+    "make_tokenflow_attention_block", "set_tokenflow", "isinstance_str", "batch_cosine_sim",
+]
+
+# --------------------------------------------------------------------------------------------
+# operator object (product: CudaOps; tests may install an oracle-backed stand-in)
+# --------------------------------------------------------------------------------------------
+_OPS = None
+
+
+def _ops():
+    global _OPS
+    if _OPS is None:
+        from .ops import CudaOps
+        _OPS = CudaOps()            # raises without the .so or without a B200: no fallback
+    return _OPS
+
+
+def _install_ops_for_testing(ops) -> None:
+    """Test seam: `tests/` may substitute an op object built on `oracle/` to exercise the hook
+    plumbing on CPU.  Pass None to restore the product path."""
+    global _OPS
+    _OPS = ops
+
+
+def _strict_dtype() -> bool:
+    """TOKENFLOW_B200_STRICT_DTYPE=1: blended frame-pass output in fp32 like the reference's
+    promoted dtype (:385-388); default fp16 (half the HBM write, same values to fp16 rounding)."""
+    return os.environ.get("TOKENFLOW_B200_STRICT_DTYPE", "0") == "1"
+
+
+# --------------------------------------------------------------------------------------------
+# module discovery (cached)
+# --------------------------------------------------------------------------------------------
+_BLOCK_CACHE: "weakref.WeakKeyDictionary[torch.nn.Module, List[torch.nn.Module]]" = weakref.WeakKeyDictionary()
+
+
+def _transformer_blocks(root: torch.nn.Module) -> List[torch.nn.Module]:
+    blocks = _BLOCK_CACHE.get(root)
+    if blocks is None:
+        blocks = [m for _, m in root.named_modules() if isinstance_str(m, "BasicTransformerBlock")]
+        _BLOCK_CACHE[root] = blocks
+    return blocks
+
+
+def _invalidate_cache(root: Optional[torch.nn.Module] = None) -> None:
+    if root is None:
+        _BLOCK_CACHE.clear()
+    else:
+        _BLOCK_CACHE.pop(root, None)
+
+
+def register_pivotal(diffusion_model, is_pivotal):
+    """Reference :7-11."""
+    for module in _transformer_blocks(diffusion_model):
+        module.pivotal_pass = is_pivotal
+
+
+def register_batch_idx(diffusion_model, batch_idx):
+    """Reference :13-17.  Frame f of the batch uses keyframes (batch_idx, batch_idx-1)."""
+    for module in _transformer_blocks(diffusion_model):
+        module.batch_idx = batch_idx
+        module._tf_frame_table = None
+
+
+def register_frame_table(diffusion_model, kf_a: Sequence[int], kf_b: Sequence[int], w: Sequence[float]):
+    """Extension for frame-granular sharding: per-frame (keyframe, previous keyframe or -1, blend
+    weight) for the frames of the next frame pass, replacing the scalar batch_idx."""
+    table = (tuple(int(a) for a in kf_a), tuple(int(b) for b in kf_b), tuple(float(x) for x in w))
+    for module in _transformer_blocks(diffusion_model):
+        module._tf_frame_table = table
+
+
+_ATTN_SITES_CACHE: "weakref.WeakKeyDictionary[torch.nn.Module, list]" = weakref.WeakKeyDictionary()
+
+
+def _timed_modules(unet) -> list:
+    """The fixed SD topology the reference hard-codes (:20-40)."""
+    mods = _ATTN_SITES_CACHE.get(unet)
+    if mods is None:
+        mods = [unet.up_blocks[1].resnets[1]]
+        for res in (1, 2, 3):
+            for block in (0, 1, 2):
+                tb = unet.up_blocks[res].attentions[block].transformer_blocks[0]
+                mods += [tb.attn1, tb.attn2]
+        for res in (0, 1, 2):
+            for block in (0, 1):
+                tb = unet.down_blocks[res].attentions[block].transformer_blocks[0]
+                mods += [tb.attn1, tb.attn2]
+        tb = unet.mid_block.attentions[0].transformer_blocks[0]
+        mods += [tb.attn1, tb.attn2]
+        _ATTN_SITES_CACHE[unet] = mods
+    return mods
+
+
+def register_time(model, t):
+    """Reference :20-40."""
+    for module in _timed_modules(model.unet):
+        module.t = t
+
+
+_LATENT_CACHE = {}
+
+
+def load_source_latents_t(t, latents_path):
+    """Reference :43-47.  The reference re-reads the full [N,4,h,w] file on every denoise_step
+    ((N/B+1) times per timestep); the tensor is kept for the current timestep instead."""
+    latents_t_path = os.path.join(latents_path, f'noisy_latents_{t}.pt')
+    assert os.path.exists(latents_t_path), f'Missing latents at t {t} path {latents_t_path}'
+    key = (latents_t_path, os.path.getmtime(latents_t_path))
+    hit = _LATENT_CACHE.get("entry")
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    latents = torch.load(latents_t_path)
+    _LATENT_CACHE["entry"] = (key, latents)
+    return latents
+
+
+# --------------------------------------------------------------------------------------------
+# injection schedules
+# --------------------------------------------------------------------------------------------
+def _in_schedule(module) -> bool:
+    """`schedule is not None and (t in schedule or t == 1000)` (reference :86, :124) without a
+    device sync: the schedule is turned into a host set once per schedule object."""
+    sched = getattr(module, "injection_schedule", None)
+    if sched is None:
+        return False
+    t = module.t
+    t = int(t) if not torch.is_tensor(t) else int(t.item())
+    if t == 1000:
+        return True
+    cached = module.__dict__.get("_tf_sched")
+    if cached is None or cached[0] is not sched:
+        values = sched.tolist() if torch.is_tensor(sched) else list(sched)
+        cached = (sched, frozenset(int(x) for x in values))
+        module.__dict__["_tf_sched"] = cached
+    return t in cached[1]
+
+
+def register_conv_injection(model, injection_schedule):
+    """Reference :49-104: PnP feature injection in up_blocks[1].resnets[1] — the residual branch of
+    the uncond and cond streams is replaced by the source stream's while t is in the schedule."""
+
+    def make_forward(res):
+        def forward(input_tensor, temb):
+            skip = input_tensor
+            h = res.nonlinearity(res.norm1(input_tensor))
+            resample = res.upsample if res.upsample is not None else res.downsample
+            if resample is not None:
+                if res.upsample is not None and h.shape[0] >= 64:
+                    skip, h = skip.contiguous(), h.contiguous()
+                skip, h = resample(skip), resample(h)
+            h = res.conv1(h)
+            if temb is not None:
+                temb = res.time_emb_proj(res.nonlinearity(temb))[:, :, None, None]
+                if res.time_embedding_norm == "default":
+                    h = h + temb
+            h = res.norm2(h)
+            if temb is not None and res.time_embedding_norm == "scale_shift":
+                scale, shift = torch.chunk(temb, 2, dim=1)
+                h = h * (1 + scale) + shift
+            h = res.conv2(res.dropout(res.nonlinearity(h)))
+            if _in_schedule(res):
+                n = h.shape[0] // 3
+                h[n:2 * n] = h[:n]          # uncond <- source   (:89)
+                h[2 * n:] = h[:n]           # cond   <- source   (:91)
+            if res.conv_shortcut is not None:
+                skip = res.conv_shortcut(skip)
+            return (skip + h) / res.output_scale_factor
+        return forward
+
+    conv_module = model.unet.up_blocks[1].resnets[1]
+    conv_module.forward = make_forward(conv_module)
+    conv_module.injection_schedule = injection_schedule
+
+
+# --------------------------------------------------------------------------------------------
+# extended attention closures
+# --------------------------------------------------------------------------------------------
+_INJECTED_SITES = {1: (1, 2), 2: (0, 1, 2), 3: (0, 1, 2)}   # reference :208, :289
+
+
+def _sa_forward(attn, pnp: bool):
+    to_out = attn.to_out[0] if type(attn.to_out) is torch.nn.modules.container.ModuleList else attn.to_out
+
+    def forward(x, encoder_hidden_states=None, attention_mask=None):
+        ctx = x if encoder_hidden_states is None else encoder_hidden_states
+        q = attn.to_q(x)
+        k = attn.to_k(ctx)
+        v = attn.to_v(ctx)
+        inject = pnp and _in_schedule(attn)
+        out = _ops().ext_attn(q, k, v, attn.heads, attn.scale, inject)
+        if not torch.is_autocast_enabled() and out.dtype != to_out.weight.dtype:
+            out = out.to(to_out.weight.dtype)       # fp16 kernel output feeding a non-autocast fp32 module
+        return to_out(out)
+
+    return forward
+
+
+def register_extended_attention_pnp(model, injection_schedule):
+    """Reference :106-214: every block's attn1 becomes extended attention; the 8 decoder sites get
+    the q/k injection schedule, all others an empty one."""
+    for module in _transformer_blocks(model.unet):
+        module.attn1.forward = _sa_forward(module.attn1, pnp=True)
+        module.attn1.injection_schedule = []
+    for res, blocks in _INJECTED_SITES.items():
+        for block in blocks:
+            attn1 = model.unet.up_blocks[res].attentions[block].transformer_blocks[0].attn1
+            attn1.forward = _sa_forward(attn1, pnp=True)
+            attn1.injection_schedule = injection_schedule
+
+
+def register_extended_attention(model):
+    """Reference :216-294 (SDEdit flavour: no injection)."""
+    for module in _transformer_blocks(model.unet):
+        module.attn1.forward = _sa_forward(module.attn1, pnp=False)
+
+
+# --------------------------------------------------------------------------------------------
+# TokenFlow block
+# --------------------------------------------------------------------------------------------
+_BLEND_CACHE = {}
+
+
+def _default_frame_table(batch_idx: int, n_frames: int):
+    """Reference :331-333 and :375-383 as a per-frame table."""
+    from .ops import blend_weights
+    w = _BLEND_CACHE.get(n_frames)
+    if w is None:
+        w = tuple(blend_weights(n_frames))
+        _BLEND_CACHE[n_frames] = w
+    kf_a = (batch_idx,) * n_frames
+    kf_b = ((batch_idx - 1) if batch_idx > 0 else -1,) * n_frames
+    return kf_a, kf_b, w
+
+
+def make_tokenflow_attention_block(block_class: Type[torch.nn.Module]) -> Type[torch.nn.Module]:
+    """Reference :296-429.  Returns a subclass of `block_class` whose forward is the TokenFlow
+    block: the pivotal pass caches norm1 features and the extended-attention output of the
+    keyframes; the frame pass skips attn1 and propagates keyframe rows along the NN field."""
+
+    class TokenFlowBlock(block_class):
+
+        def forward(self, hidden_states, attention_mask=None, encoder_hidden_states=None,
+                    encoder_attention_mask=None, timestep=None, cross_attention_kwargs=None,
+                    class_labels=None) -> torch.Tensor:
+            if getattr(self, "use_ada_layer_norm", False) or getattr(self, "use_ada_layer_norm_zero", False):
+                raise NotImplementedError(
+                    "tokenflow_b200: AdaLayerNorm transformer blocks are not part of any Stable-Diffusion "
+                    "UNet and are not supported by the B200 hot path")
+            batch_size, sequence_length, dim = hidden_states.shape
+            n_frames = batch_size // 3
+            ops = _ops()
+            norm_hidden_states = self.norm1(hidden_states)
+            cross_attention_kwargs = cross_attention_kwargs if cross_attention_kwargs is not None else {}
+
+            if self.pivotal_pass:
+                # cache keyframe features (:326-327) — plus their fp16 unit rows for the NN field
+                self.pivot_hidden_states = norm_hidden_states.view(3, n_frames, sequence_length, dim)
+                self._tf_pivot_unit = ops.unit_rows(self.pivot_hidden_states[0])
+                self.attn_output = self.attn1(
+                    norm_hidden_states,
+                    encoder_hidden_states=encoder_hidden_states if self.only_cross_attention else None,
+                    **cross_attention_kwargs)
+                self.kf_attn_output = self.attn_output                                   # :360
+                hidden_states = self.attn_output + hidden_states                          # :397
+            else:
+                table = getattr(self, "_tf_frame_table", None)
+                if table is None:
+                    table = _default_frame_table(self.batch_idx, n_frames)
+                kf_a, kf_b, w = table
+                if len(kf_a) != n_frames:
+                    raise ValueError(f"frame table has {len(kf_a)} entries but the pass has {n_frames} frames")
+                kf = self.kf_attn_output
+                n_kf = kf.shape[0] // 3
+                x_unit = ops.unit_rows(norm_hidden_states[:n_frames])                    # source stream only (:335)
+                idx_a, idx_b = ops.nn_field(x_unit, self._tf_pivot_unit, kf_a, kf_b)      # :335-343
+                out_dtype = torch.float32 if (_strict_dtype() and idx_b is not None) else None
+                hidden_states = ops.propagate(kf.view(3, n_kf, sequence_length, dim), idx_a, idx_b, kf_a, kf_b, w,
+                                              residual=hidden_states, out_dtype=out_dtype)   # :361-397
+                self._tf_nn_idx = (idx_a, idx_b)
+
+            if self.attn2 is not None:
+                attn_output = self.attn2(self.norm2(hidden_states), encoder_hidden_states=encoder_hidden_states,
+                                         attention_mask=encoder_attention_mask, **cross_attention_kwargs)
+                hidden_states = attn_output + hidden_states
+            return self.ff(self.norm3(hidden_states)) + hidden_states
+
+    return TokenFlowBlock
+
+
+def set_tokenflow(model: torch.nn.Module):
+    """Reference :432-448: swap every BasicTransformerBlock's class for the TokenFlow subclass."""
+    _invalidate_cache()
+    made = {}
+    for _, module in model.named_modules():
+        if isinstance_str(module, "BasicTransformerBlock") and not isinstance_str(module, "TokenFlowBlock"):
+            cls = module.__class__
+            if cls not in made:
+                made[cls] = make_tokenflow_attention_block(cls)
+            module.__class__ = made[cls]
+            if not hasattr(module, "use_ada_layer_norm_zero"):
+                module.use_ada_layer_norm = False
+                module.use_ada_layer_norm_zero = False
+    return model
