@@ -54,8 +54,10 @@ class OracleOps:
             a1 = A[:, int(kf_a[f])][:, idx_a[f].long()]                 # [3, S, dim]
             if int(kf_b[f]) >= 0:
                 a2 = A[:, int(kf_b[f])][:, idx_b[f].long()]
-                wf = torch.tensor(float(w[f]), dtype=torch.float32, device=A.device)
-                a1 = wf * a1 + (1 - wf) * a2                            # reference :388 (fp32 weight promotes)
+                # a dimensioned fp32 weight tensor, like the reference's w1.repeat(3,1,S,dim) (:385):
+                # it promotes the fp16 rows to fp32 (a 0-dim tensor would not)
+                wf = torch.full((1, 1, 1), float(w[f]), dtype=torch.float32, device=A.device)
+                a1 = wf * a1 + (1 - wf) * a2                            # reference :388
             outs.append(a1)
         out = torch.stack(outs, dim=1).reshape(3 * F_, S, dim)
         if residual is not None:

@@ -79,7 +79,10 @@ def test_propagate_bit_exact(ops, F, K, S, dim, batch, with_residual):
     kf_a, kf_b, w = [batch] * F, [batch - 1 if batch > 0 else -1] * F, blend_weights(F)
     ref = OracleOps().propagate(A, idx_a, idx_b, kf_a, kf_b, w, res)         # fp32 when blended
     got32 = ops.propagate(A, idx_a, idx_b, kf_a, kf_b, w, res, out_dtype=torch.float32)
-    assert torch.equal(got32, ref.float())
+    if ref.dtype == torch.float32:        # blended: the reference's promoted dtype, bit for bit
+        assert torch.equal(got32, ref)
+    else:                                 # batch 0: the reference stays in fp16 (fp32 add, one rounding)
+        assert torch.equal(got32.half(), ref)
     got16 = ops.propagate(A, idx_a, idx_b, kf_a, kf_b, w, res)
     assert got16.dtype == torch.float16 and torch.equal(got16, ref.half())
 
@@ -232,7 +235,9 @@ def test_ext_attn_peaky_softmax(ops):
     v = torch.randn(3 * n, S, heads * d, device="cuda").half()
     got = ops.ext_attn(q, k, v, heads, d ** -0.5, False)
     want = _attn_ref(q, k, v, heads, d ** -0.5, False)
-    assert (got.float() - want).abs().max().item() < 2e-3
+    # near one-hot softmax: outputs approach raw |v| ~ 3, where one fp16 ulp is already 2e-3 —
+    # the 1e-3 bound applies at unit magnitude and scales with the fp16 spacing above it
+    assert torch.allclose(got.float(), want, atol=1e-3, rtol=1.5e-3)
 
 
 def test_ext_attn_golden(ops, golden_dir):

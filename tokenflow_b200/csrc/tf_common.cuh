@@ -84,14 +84,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug becomes a trap (launch error reported to the host) instead of a
-// hung GPU.  The bound (~2^28 polls of a HW-suspended try_wait) is far beyond any legal wait.
+// hung GPU.  No legal wait in these kernels lasts longer than a few milliseconds; the bound is 2 s
+// of wall clock (%globaltimer, sampled every 2048 failed polls).
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 28)) {
-      printf("tokenflow_b200: mbarrier wait timed out (block %d thread %d bar %p parity %u)\n",
-             (int)blockIdx.x, (int)threadIdx.x, (void*)bar, parity);
-      __trap();
+    if ((++spins & 2047u) == 0) {
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 2000000000ull) {
+        printf("tokenflow_b200: mbarrier wait timed out (block %d thread %d smem 0x%x parity %u)\n",
+               (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
+        __trap();
+      }
     }
   }
 }
