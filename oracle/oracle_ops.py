@@ -68,3 +68,19 @@ class OracleOps:
 
     def ext_attn(self, q, k, v, heads: int, scale: float, inject: bool) -> torch.Tensor:
         return O.extended_attention(q, k, v, heads, scale, inject)
+
+    def ext_attn_table(self, q, k, v, table, heads: int, scale: float) -> torch.Tensor:
+        """Sharded-pass form: output sample j attends with q[qs] to the nkv consecutive slabs
+        k[k0:k0+nkv], v[v0:v0+nkv] (frame-major), per head — the same per-head softmax(q k^T scale) v
+        as reference :173-179."""
+        _, S, dim = q.shape
+        d = dim // heads
+        outs = []
+        for (qs, k0, v0, nkv) in table:
+            qq = q[qs].reshape(S, heads, d).permute(1, 0, 2)
+            kk = k[k0:k0 + nkv].reshape(nkv * S, heads, d).permute(1, 0, 2)
+            vv = v[v0:v0 + nkv].reshape(nkv * S, heads, d).permute(1, 0, 2)
+            sim = torch.bmm(qq, kk.transpose(-1, -2)) * scale
+            o = torch.bmm(sim.softmax(dim=-1), vv)
+            outs.append(o.permute(1, 0, 2).reshape(S, dim))
+        return torch.stack(outs)

@@ -5,7 +5,7 @@
 //
 // HBM-bound byte mover.  What the reference does with ~10x the algorithmic traffic (two int64
 // [3,B*S,dim] index tensors, an fp32 [3,B,S,dim] weight tensor, 6 elementwise passes; SURVEY.md
-// §2.1 k10-k12) is one pass here: each thread owns one 16-byte vector of one token row, reads the
+// §2.1 k10-k12) is one pass here: each thread owns one 16-byte vector column of a token row, reads the
 // two int32 NN indices once and reuses them for the three streams, issues all (up to 9) independent
 // 16-byte loads before the first use, blends in fp32 and stores the row once.  Consecutive threads
 // own consecutive vectors of the contiguous [f,p,dim] output, so stores and residual loads are
@@ -21,7 +21,7 @@ namespace tf {
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 320;   // 8 x 40, 4 x 80, 2 x 160 vectors: whole rows for every SD channel width
 
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) {   // read-once data: keep it out of L1
   uint4 r;
@@ -54,32 +54,37 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return v;
 }
 
+// Thread layout: blockIdx.y = frame; inside a block, threadIdx.x -> (row-in-group, 16-byte vector) with
+// the vector index fixed per thread, so the row loop has no integer division and consecutive
+// threads cover consecutive 16-byte vectors of consecutive output rows (fully coalesced).
 template <bool kOutF32, bool kResidual>
 __global__ void __launch_bounds__(kThreads)
 propagate_kernel(const __half* __restrict__ A, const int32_t* __restrict__ idx_a,
                  const int32_t* __restrict__ idx_b, FrameTable tab, int F, int S, int dim, int K,
-                 const __half* __restrict__ residual, void* __restrict__ out) {
-  const int nvec = dim >> 3;                               // 16-byte vectors per row
-  const long long rows = (long long)F * S;
-  const long long total = rows * nvec;
-  const long long stream_out = rows * dim;                 // elements per stream in out / residual
-  const long long kf_stride = (long long)S * dim;          // elements per keyframe slab
+                 const __half* __restrict__ residual, void* __restrict__ out, int nvec, int rows_per_block) {
+  const int f = blockIdx.y;
+  const int r_in = threadIdx.x / nvec;
+  const int vec = threadIdx.x - r_in * nvec;
+  if (r_in >= rows_per_block) return;
+  const int kfa = tab.kf_a[f];
+  const int kfb = tab.kf_b[f];
+  const float w = tab.w[f];
+  const float w2 = 1.0f - w;
+  const long long stream_out = (long long)F * S * dim;      // elements per stream in out / residual
+  const long long kf_stride = (long long)S * dim;           // elements per keyframe slab
   const long long stream_A = (long long)K * kf_stride;
+  const __half* A_a = A + (long long)kfa * kf_stride + vec * 8;
+  const __half* A_b = A + (long long)(kfb >= 0 ? kfb : kfa) * kf_stride + vec * 8;
+  const int32_t* ia_f = idx_a + (long long)f * S;
+  const int32_t* ib_f = idx_b + (long long)f * S;
+  const long long frame_off = (long long)f * S * dim + vec * 8;
 
-  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total;
-       i += (long long)gridDim.x * kThreads) {
-    const long long row = i / nvec;
-    const int vec = (int)(i - row * nvec);
-    const int f = (int)(row / S);
-    const int kfa = tab.kf_a[f];
-    const int kfb = tab.kf_b[f];
-    const float w = tab.w[f];
-    const int ia = __ldg(idx_a + row);
-    const int ib = (kfb >= 0) ? __ldg(idx_b + row) : 0;
-
-    const __half* a_row = A + (long long)kfa * kf_stride + (long long)ia * dim + vec * 8;
-    const __half* b_row = A + (long long)(kfb >= 0 ? kfb : kfa) * kf_stride + (long long)ib * dim + vec * 8;
-    const long long o_off = row * dim + vec * 8;
+  for (int p = blockIdx.x * rows_per_block + r_in; p < S; p += gridDim.x * rows_per_block) {
+    const int ia = __ldg(ia_f + p);
+    const int ib = (kfb >= 0) ? __ldg(ib_f + p) : 0;
+    const __half* a_row = A_a + (long long)ia * dim;
+    const __half* b_row = A_b + (long long)ib * dim;
+    const long long o_off = frame_off + (long long)p * dim;
 
     uint4 va[3], vb[3], vr[3];
 #pragma unroll
@@ -95,7 +100,6 @@ propagate_kernel(const __half* __restrict__ A, const int32_t* __restrict__ idx_a
       if (kfb >= 0) {
         float b[8];
         unpack8(vb[s], b);
-        const float w2 = 1.0f - w;
 #pragma unroll
         for (int e = 0; e < 8; ++e)   // reference :388: two fp32 products then an fp32 add (no FMA contraction)
           a[e] = __fadd_rn(__fmul_rn(w, a[e]), __fmul_rn(w2, b[e]));
@@ -121,17 +125,24 @@ propagate_kernel(const __half* __restrict__ A, const int32_t* __restrict__ idx_a
 int launch_propagate(const void* A, const int32_t* idx_a, const int32_t* idx_b, const FrameTable& tab, int F,
                      int S, int dim, int K, const void* residual, void* out, int out_is_f32,
                      cudaStream_t stream) {
-  const long long total = (long long)F * S * (dim >> 3);
-  if (total == 0) return TF_OK;
-  // one wave of resident CTAs (8 x 256 threads per SM), grid-stride over the rest
-  long long blocks = (total + kThreads - 1) / kThreads;
-  const long long cap = (long long)sm_count() * 8;
-  if (blocks > cap) blocks = cap;
-  dim3 grid((unsigned)blocks), block(kThreads);
+  if ((long long)F * S == 0) return TF_OK;
+  const int nvec = dim >> 3;
+  if (nvec > kThreads) {
+    set_last_error("tf_propagate: dim=%d > %d is not supported", dim, kThreads * 8);
+    return TF_ERR_UNSUPPORTED;
+  }
+  const int rows_per_block = kThreads / nvec;
+  // about one wave of resident CTAs in total (6 CTAs of 320 threads per SM), split evenly over frames
+  int bx = (S + rows_per_block - 1) / rows_per_block;
+  const int cap = (sm_count() * 6 + F - 1) / F;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  dim3 grid((unsigned)bx, (unsigned)F), block(kThreads);
   const __half* Ah = static_cast<const __half*>(A);
   const __half* Rh = static_cast<const __half*>(residual);
 #define TF_LAUNCH(OUTF32, RES)                                                                         \
-  propagate_kernel<OUTF32, RES><<<grid, block, 0, stream>>>(Ah, idx_a, idx_b, tab, F, S, dim, K, Rh, out)
+  propagate_kernel<OUTF32, RES><<<grid, block, 0, stream>>>(Ah, idx_a, idx_b, tab, F, S, dim, K, Rh, out, nvec, \
+                                                            rows_per_block)
   if (out_is_f32) {
     if (residual) TF_LAUNCH(true, true); else TF_LAUNCH(true, false);
   } else {

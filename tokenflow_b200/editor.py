@@ -26,7 +26,8 @@ import torch.nn as nn
 
 class TokenFlowEditor(nn.Module):
     def __init__(self, unet: nn.Module, scheduler, hooks, config: Dict, text_embeds: torch.Tensor,
-                 pnp_guidance_embeds: torch.Tensor, source_latents: Optional[Callable[[int], torch.Tensor]] = None):
+                 pnp_guidance_embeds: torch.Tensor, source_latents: Optional[Callable[[int], torch.Tensor]] = None,
+                 world_size: int = 1, rank: int = 0, group=None):
         """config keys (names follow configs/config_pnp.yaml): n_frames, batch_size, n_timesteps,
         guidance_scale, mode ('pnp' | 'sdedit'), pnp_attn_t, pnp_f_t, start (sdedit), latents_path.
         text_embeds: [2, L, C] (uncond, cond);  pnp_guidance_embeds: [1, L, C] (inversion prompt)."""
@@ -45,6 +46,8 @@ class TokenFlowEditor(nn.Module):
             start = float(self.config.get("start", 0.9))
             self.scheduler.timesteps = self.scheduler.timesteps[int(1 - start * self.config["n_timesteps"]):]
         self.keyframe_log = []
+        self.world_size, self.rank, self.group = world_size, rank, group
+        self._src_override = None
 
     # ------------------------------------------------------------------------------------
     def init_method(self):
@@ -63,6 +66,8 @@ class TokenFlowEditor(nn.Module):
         h.set_tokenflow(self.unet)
 
     def source_latents_t(self, t: int) -> torch.Tensor:
+        if self._src_override is not None and self._src_override[0] == int(t):
+            return self._src_override[1]
         if self._source_latents is not None:
             return self._source_latents(t)
         return self.hooks.load_source_latents_t(t, self.latents_path)
@@ -92,7 +97,10 @@ class TokenFlowEditor(nn.Module):
         return torch.randint(batch_size, (n // batch_size,)) + torch.arange(0, n, batch_size)
 
     def batched_denoise_step(self, x, t, indices):
-        """run_tokenflow_pnp.py:220-233."""
+        """run_tokenflow_pnp.py:220-233 (one process), or its frame-sharded form (world_size > 1)."""
+        if self.world_size > 1:
+            with self._autocast():
+                return self._sharded_step(x, t, indices)
         h = self.hooks
         batch_size = self.config["batch_size"]
         with self._autocast():
@@ -106,6 +114,76 @@ class TokenFlowEditor(nn.Module):
                 h.register_batch_idx(self, i)
                 denoised.append(self.denoise_step(x[b:b + batch_size], t, indices[b:b + batch_size]))
             return torch.cat(denoised)
+
+    # ------------------------------------------------------------------------------------
+    # multi-GPU: one process per GPU, frames sharded, keyframe tensors all-gathered
+    # ------------------------------------------------------------------------------------
+    def frame_table(self, frames):
+        """Per-frame (keyframe, previous keyframe, blend weight) for global frame ids — the reference's
+        batch_idx arithmetic (tokenflow_utils.py:331-333, :375-383) evaluated per frame."""
+        from .ops import blend_weights
+        B = self.config["batch_size"]
+        w = blend_weights(B)
+        kf_a = [g // B for g in frames]
+        kf_b = [(g // B) - 1 if g >= B else -1 for g in frames]
+        return kf_a, kf_b, [w[g % B] for g in frames]
+
+    @torch.no_grad()
+    def _sharded_step(self, x, t, indices):
+        import torch.distributed as dist
+        h, G, r = self.hooks, self.world_size, self.rank
+        N, B = len(x), self.config["batch_size"]
+        K = N // B
+        assert N % G == 0, "frames must divide evenly over the ranks"
+        pivotal_idx = self.draw_keyframes(N)                  # same CPU seed on every rank -> same keyframes
+        self.keyframe_log.append(pivotal_idx.tolist())
+        src_all = self.source_latents_t(int(t))[indices].to(x.device, x.dtype)
+        h.register_time(self, int(t))
+        # ---- pivotal pass: this rank's m of the 3K (stream, keyframe) samples ----
+        shard = h.PivotalShard(G, r, K, self.group)
+        lat, emb = [], []
+        for i in shard.slots:
+            i = min(i, 3 * K - 1)                             # padding slots recompute the last sample
+            s, f = divmod(i, K)
+            frame = int(pivotal_idx[f])
+            lat.append(src_all[frame] if s == 0 else x[frame])
+            emb.append(self.pnp_guidance_embeds[0] if s == 0 else self.text_embeds[s - 1])
+        h.register_shard(self, shard)
+        h.register_pivotal(self, True)
+        self.unet(torch.stack(lat), t, encoder_hidden_states=torch.stack(emb))
+        h.register_pivotal(self, False)
+        h.register_shard(self, None)
+        # ---- frame pass: this rank's contiguous frames, per-frame keyframe table ----
+        per = N // G
+        frames = list(range(r * per, (r + 1) * per))
+        h.register_frame_table(self, *self.frame_table(frames))
+        xs = x[frames[0]:frames[-1] + 1]
+        latent_model_input = torch.cat([src_all[frames[0]:frames[-1] + 1], xs, xs])
+        text = torch.cat([self.pnp_guidance_embeds.repeat(per, 1, 1), torch.repeat_interleave(self.text_embeds, per, dim=0)])
+        noise_pred = self.unet(latent_model_input, t, encoder_hidden_states=text)['sample']
+        _, npu, npc = noise_pred.chunk(3)
+        noise_pred = npu + self.config["guidance_scale"] * (npc - npu)
+        x_local = self.scheduler.step(noise_pred, t, xs)['prev_sample'].contiguous()
+        out = torch.empty_like(x)
+        dist.all_gather_into_tensor(out, x_local, group=self.group)
+        return out
+
+    # ------------------------------------------------------------------------------------
+    # host-buffer entry point (bench `e2e`): latents live in pinned host memory
+    # ------------------------------------------------------------------------------------
+    def edit_step_host(self, x_host: torch.Tensor, src_host_t: torch.Tensor, t: int, out_host: torch.Tensor):
+        """One denoising step with HOST latents: H2D of this step's noisy latents and source latents,
+        the step, D2H of the denoised latents, stream-synchronised before returning."""
+        x = x_host.to(self.device, non_blocking=True)
+        self._src_override = (int(t), src_host_t.to(self.device, non_blocking=True))
+        try:
+            y = self.batched_denoise_step(x, torch.tensor(int(t), device=self.device), torch.arange(len(x_host)))
+        finally:
+            self._src_override = None
+        out_host.copy_(y, non_blocking=True)
+        if self.device.type == "cuda":
+            torch.cuda.current_stream().synchronize()
+        return out_host
 
     def sample_loop(self, x, indices=None, on_step: Optional[Callable] = None):
         """run_tokenflow_pnp.py:264-273 without the VAE decode."""

@@ -89,6 +89,16 @@ def blend_weights(n_frames: int) -> Sequence[float]:
     return torch.sigmoid(d2 / (d1 + d2)).tolist()
 
 
+def propagate_bytes(F_: int, S: int, dim: int, kf_a, kf_b, with_residual: bool, out_esz: int = 2) -> float:
+    """Algorithmic HBM bytes of one tf_propagate launch (DESIGN.md / SURVEY.md §8d): output write +
+    residual read + each referenced keyframe slab once for the three streams + the int32 indices.
+    Re-touched keyframe rows are L2 hits and are not counted."""
+    kfs = {int(a) for a in kf_a} | {int(b) for b in kf_b if int(b) >= 0}
+    n_idx = F_ + sum(1 for b in kf_b if int(b) >= 0)
+    return (3.0 * F_ * S * dim * out_esz + (3.0 * F_ * S * dim * 2 if with_residual else 0.0)
+            + 3.0 * len(kfs) * S * dim * 2 + 4.0 * S * n_idx)
+
+
 def _i32(vals: Sequence[int]):
     return (ctypes.c_int32 * len(vals))(*[int(v) for v in vals])
 
@@ -124,6 +134,38 @@ class CudaOps:
     def launch_count(self) -> int:
         return int(self.lib.tf_launch_count())
 
+    # -- optional per-launch CUDA-event timing (bench.py's live roofline measurement) ------------
+    _timing = None
+
+    def enable_timing(self, on: bool = True):
+        """When on, every kernel launch is bracketed by CUDA events recorded on the launching
+        (current) stream; `timing_summary()` synchronises and aggregates them per kernel."""
+        self._timing = [] if on else None
+
+    def _timed(self, name: str, work: float, fn):
+        if self._timing is None:
+            return fn()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        out = fn()
+        end.record()
+        self._timing.append((name, float(work), start, end))
+        return out
+
+    def timing_summary(self):
+        """{kernel: {"launches", "ms", "work"}}; `work` = algorithmic flops (tensor-bound kernels)
+        or bytes (HBM-bound kernels) summed over launches."""
+        torch.cuda.synchronize()
+        agg = {}
+        for name, work, s, e in (self._timing or []):
+            a = agg.setdefault(name, {"launches": 0, "ms": 0.0, "work": 0.0})
+            a["launches"] += 1
+            a["ms"] += s.elapsed_time(e)
+            a["work"] += work
+        if self._timing is not None:
+            self._timing = []
+        return agg
+
     # -- operators -------------------------------------------------------------------------
     def unit_rows(self, x: torch.Tensor) -> torch.Tensor:
         """[..., dim] fp32/fp16 → fp16 unit rows (reference util.py:66-67 + autocast fp16 cast)."""
@@ -134,8 +176,10 @@ class CudaOps:
         if x2.stride(-1) != 1:
             x2 = x2.contiguous()
         out = torch.empty(x2.shape, dtype=torch.float16, device=x.device)
-        self._check(self.lib.tf_unit_rows(x2.data_ptr(), int(x2.dtype == torch.float32), x2.shape[0], dim,
-                                          x2.stride(0), out.data_ptr(), self._stream()), "tf_unit_rows")
+        nbytes = x2.shape[0] * dim * (x2.element_size() + 2)
+        self._timed("tf_unit_rows", nbytes, lambda: self._check(
+            self.lib.tf_unit_rows(x2.data_ptr(), int(x2.dtype == torch.float32), x2.shape[0], dim,
+                                  x2.stride(0), out.data_ptr(), self._stream()), "tf_unit_rows"))
         return out.view(*x.shape)
 
     def nn_field(self, x_unit: torch.Tensor, piv_unit: torch.Tensor, kf_a: Sequence[int],
@@ -152,10 +196,11 @@ class CudaOps:
         idx_b = torch.empty((F_, S), dtype=torch.int32, device=x_unit.device) if any_b else None
         for f0 in range(0, F_, TF_MAX_FRAMES):
             f1 = min(F_, f0 + TF_MAX_FRAMES)
-            self._check(self.lib.tf_nn_field(
+            pairs = (f1 - f0) + sum(1 for b in kf_b[f0:f1] if int(b) >= 0)
+            self._timed("tf_nn_field", 2.0 * pairs * S * S * dim, lambda: self._check(self.lib.tf_nn_field(
                 x_unit[f0:f1].data_ptr(), piv_unit.data_ptr(), _i32(kf_a[f0:f1]), _i32(kf_b[f0:f1]), f1 - f0, S, dim,
                 K, idx_a[f0:f1].data_ptr(), idx_b[f0:f1].data_ptr() if idx_b is not None else None,
-                self._stream()), "tf_nn_field")
+                self._stream()), "tf_nn_field"))
         return idx_a, idx_b
 
     def propagate(self, A: torch.Tensor, idx_a: torch.Tensor, idx_b: Optional[torch.Tensor],
@@ -174,10 +219,12 @@ class CudaOps:
         out = torch.empty((3, F_, S, dim), dtype=out_dtype, device=A.device)
         assert out_dtype in (torch.float16, torch.float32)
         if F_ <= TF_MAX_FRAMES:
-            self._check(self.lib.tf_propagate(
-                A.data_ptr(), idx_a.data_ptr(), idx_b.data_ptr() if idx_b is not None else None, _i32(kf_a),
-                _i32(kf_b), _f32(w), F_, S, dim, K, residual.data_ptr() if residual is not None else None,
-                out.data_ptr(), int(out_dtype == torch.float32), self._stream()), "tf_propagate")
+            self._timed("tf_propagate", propagate_bytes(F_, S, dim, kf_a, kf_b, residual is not None,
+                                                        out.element_size()), lambda: self._check(
+                self.lib.tf_propagate(
+                    A.data_ptr(), idx_a.data_ptr(), idx_b.data_ptr() if idx_b is not None else None, _i32(kf_a),
+                    _i32(kf_b), _f32(w), F_, S, dim, K, residual.data_ptr() if residual is not None else None,
+                    out.data_ptr(), int(out_dtype == torch.float32), self._stream()), "tf_propagate"))
         else:  # the [3,F,S,dim] layout is not sliceable along F without strides: chunk through temporaries
             for f0 in range(0, F_, TF_MAX_FRAMES):
                 f1 = min(F_, f0 + TF_MAX_FRAMES)
@@ -205,7 +252,26 @@ class CudaOps:
             q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
             tok = dim
         out = torch.empty((b, S, dim), dtype=torch.float16, device=q.device)
-        self._check(self.lib.tf_ext_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), tok, n, S, heads, d,
-                                             float(scale), int(bool(inject)), out.data_ptr(), self._stream()),
-                    "tf_ext_attn_fwd")
+        flops = 4.0 * n * S * S * dim * (2 * n + 1)        # QK^T + PV; source: S keys, uncond+cond: n*S keys
+        self._timed("tf_ext_attn", flops, lambda: self._check(
+            self.lib.tf_ext_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), tok, n, S, heads, d,
+                                     float(scale), int(bool(inject)), out.data_ptr(), self._stream()),
+            "tf_ext_attn_fwd"))
+        return out
+
+    def ext_attn_table(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, table, heads: int,
+                       scale: float) -> torch.Tensor:
+        """General form (sharded pivotal pass): `table[j] = (q slab, first k slab, first v slab, number of
+        consecutive key slabs)` for output sample j.  q [Q,S,dim], k/v [KV,S,dim] fp16 → [len(table),S,dim]."""
+        _, S, dim = q.shape
+        d = dim // heads
+        q, k, v = (t.to(torch.float16).contiguous() for t in (q, k, v))
+        n_out = len(table)
+        out = torch.empty((n_out, S, dim), dtype=torch.float16, device=q.device)
+        flops = sum(4.0 * S * (nkv * S) * dim for (_, _, _, nkv) in table)
+        self._timed("tf_ext_attn", flops, lambda: self._check(self.lib.tf_ext_attn_fwd_table(
+            q.data_ptr(), q.shape[0], dim, k.data_ptr(), v.data_ptr(), k.shape[0], dim, n_out,
+            _i32(range(n_out)), _i32([t[0] for t in table]), _i32([t[1] for t in table]),
+            _i32([t[2] for t in table]), _i32([t[3] for t in table]), S, heads, d, float(scale), out.data_ptr(),
+            self._stream()), "tf_ext_attn_fwd_table"))
         return out

@@ -32,7 +32,8 @@ import torch
 from .util import isinstance_str, batch_cosine_sim  # noqa: F401  (re-exported like the reference)
 
 __all__ = [
-    "register_pivotal", "register_batch_idx", "register_frame_table", "register_time", "load_source_latents_t",
+    "register_pivotal", "register_batch_idx", "register_frame_table", "register_shard", "PivotalShard",
+    "register_time", "load_source_latents_t",
     "register_conv_injection", "register_extended_attention_pnp", "register_extended_attention",
     "make_tokenflow_attention_block", "set_tokenflow", "isinstance_str", "batch_cosine_sim",
 ]
@@ -104,6 +105,52 @@ def register_frame_table(diffusion_model, kf_a: Sequence[int], kf_b: Sequence[in
     table = (tuple(int(a) for a in kf_a), tuple(int(b) for b in kf_b), tuple(float(x) for x in w))
     for module in _transformer_blocks(diffusion_model):
         module._tf_frame_table = table
+
+
+class PivotalShard:
+    """Multi-GPU pivotal pass.  The 3K (stream, keyframe) samples of the pass, in the
+    reference's batch order i = stream*K + keyframe, are dealt to the G ranks in contiguous groups of
+    m = ceil(3K/G) slots (the tail is padded with dummy samples); an all-gather along that axis
+    therefore reproduces the reference's [3K, S, dim] layout in its first 3K slabs.  Collectives go
+    through torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, world_size: int, rank: int, n_keyframes: int, group=None):
+        self.world_size, self.rank, self.K, self.group = world_size, rank, n_keyframes, group
+        self.m = -(-3 * n_keyframes // world_size)
+        self.slots = list(range(rank * self.m, (rank + 1) * self.m))     # global sample ids (>= 3K: padding)
+
+    def all_gather(self, t: torch.Tensor) -> torch.Tensor:
+        import torch.distributed as dist
+        t = t.contiguous()
+        out = torch.empty((self.world_size * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t, group=self.group)
+        return out
+
+    def attention_table(self, inject: bool):
+        """Per local slot: (q slab, first k slab, first v slab, number of key slabs) in the coordinates of
+        the gathered K/V (global sample order); q is global when injecting (the source stream's q may live
+        on another rank), local otherwise.  Reference :124-138."""
+        K, tab = self.K, []
+        for j, i in enumerate(self.slots):
+            if i >= 3 * K:                       # padding slot: harmless self-attention on its own slab
+                tab.append((i if inject else j, i, i, 1))
+                continue
+            s, f = divmod(i, K)
+            if s == 0:
+                tab.append((i if inject else j, i, i, 1))
+            else:
+                tab.append((f if inject else j, 0 if inject else s * K, s * K, K))
+        return tab
+
+
+def register_shard(diffusion_model, shard: Optional[PivotalShard]):
+    """Install (or clear, with None) the multi-GPU pivotal-pass context on every TokenFlow block."""
+    for module in _transformer_blocks(diffusion_model):
+        module._tf_shard = shard
+        module.attn1._tf_shard = shard
+    unet = getattr(diffusion_model, "unet", None)
+    if unet is not None:
+        unet.up_blocks[1].resnets[1]._tf_shard = shard       # PnP conv-feature injection site
 
 
 _ATTN_SITES_CACHE: "weakref.WeakKeyDictionary[torch.nn.Module, list]" = weakref.WeakKeyDictionary()
@@ -196,9 +243,15 @@ def register_conv_injection(model, injection_schedule):
                 h = h * (1 + scale) + shift
             h = res.conv2(res.dropout(res.nonlinearity(h)))
             if _in_schedule(res):
-                n = h.shape[0] // 3
-                h[n:2 * n] = h[:n]          # uncond <- source   (:89)
-                h[2 * n:] = h[:n]           # cond   <- source   (:91)
+                shard = getattr(res, "_tf_shard", None)
+                if shard is None:
+                    n = h.shape[0] // 3
+                    h[n:2 * n] = h[:n]          # uncond <- source   (:89)
+                    h[2 * n:] = h[:n]           # cond   <- source   (:91)
+                else:                           # sharded pivotal pass: the source sample may be remote
+                    h_all = shard.all_gather(h)
+                    src = [i % shard.K if i < 3 * shard.K else i for i in shard.slots]
+                    h = h_all[src]
             if res.conv_shortcut is not None:
                 skip = res.conv_shortcut(skip)
             return (skip + h) / res.output_scale_factor
@@ -224,7 +277,13 @@ def _sa_forward(attn, pnp: bool):
         k = attn.to_k(ctx)
         v = attn.to_v(ctx)
         inject = pnp and _in_schedule(attn)
-        out = _ops().ext_attn(q, k, v, attn.heads, attn.scale, inject)
+        shard = getattr(attn, "_tf_shard", None)
+        if shard is None:
+            out = _ops().ext_attn(q, k, v, attn.heads, attn.scale, inject)
+        else:                                    # keyframe K/V (and, when injecting, Q) all-gathered over NVLink
+            k_all, v_all = shard.all_gather(k), shard.all_gather(v)
+            q_src = shard.all_gather(q) if inject else q
+            out = _ops().ext_attn_table(q_src, k_all, v_all, shard.attention_table(inject), attn.heads, attn.scale)
         if not torch.is_autocast_enabled() and out.dtype != to_out.weight.dtype:
             out = out.to(to_out.weight.dtype)       # fp16 kernel output feeding a non-autocast fp32 module
         return to_out(out)
@@ -289,7 +348,16 @@ def make_tokenflow_attention_block(block_class: Type[torch.nn.Module]) -> Type[t
             norm_hidden_states = self.norm1(hidden_states)
             cross_attention_kwargs = cross_attention_kwargs if cross_attention_kwargs is not None else {}
 
-            if self.pivotal_pass:
+            shard = getattr(self, "_tf_shard", None)
+            if self.pivotal_pass and shard is not None:
+                # sharded pivotal pass: this rank holds m of the 3K (stream, keyframe) samples
+                unit_all = shard.all_gather(ops.unit_rows(norm_hidden_states))
+                self._tf_pivot_unit = unit_all[:shard.K]                                  # source stream
+                self.pivot_hidden_states = norm_hidden_states
+                self.attn_output = self.attn1(norm_hidden_states, **cross_attention_kwargs)
+                self.kf_attn_output = shard.all_gather(self.attn_output)[:3 * shard.K]
+                hidden_states = self.attn_output + hidden_states
+            elif self.pivotal_pass:
                 # cache keyframe features (:326-327) — plus their fp16 unit rows for the NN field
                 self.pivot_hidden_states = norm_hidden_states.view(3, n_frames, sequence_length, dim)
                 self._tf_pivot_unit = ops.unit_rows(self.pivot_hidden_states[0])
