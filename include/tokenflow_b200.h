@@ -47,6 +47,15 @@ int64_t tf_launch_count(void);
 int tf_unit_rows(const void* x, int x_is_f32, int64_t rows, int dim, int64_t x_row_stride, void* out_f16,
                  tf_stream_t stream);
 
+/* norm1 fused with the row normalisation, for the frame pass: out = fp16(LN(x) / ||LN(x)||_2) with the
+ * LayerNorm evaluated in fp32 like autocast does (tokenflow_utils.py:323 norm1 + util.py:66-67).  Only
+ * the source stream's rows are needed there (reference :335), so callers pass that third only.
+ *   x_f16        device [rows, dim] fp16, row pitch `x_row_stride` elements (multiple of 8)
+ *   gamma, beta  device [dim] fp32 (norm1.weight / norm1.bias), eps = norm1.eps
+ *   out_f16      device [rows, dim] fp16 contiguous;  dim <= 1280 */
+int tf_layernorm_unit_rows(const void* x_f16, int64_t rows, int dim, int64_t x_row_stride, const float* gamma,
+                           const float* beta, float eps, void* out_f16, tf_stream_t stream);
+
 /* Token nearest-neighbour field.  Replaces tokenflow_utils.py:329-348 (+ util.py:68 `x @ y.T`,
  * fp16 output under autocast, and the two argmax reductions :340-343):
  *   idx_a[f,p] = argmax_c fp16( x_unit[f,p,:] . piv_unit[kf_a[f],c,:] )     first index on ties

@@ -27,6 +27,9 @@ class OracleOps:
     def unit_rows(self, x: torch.Tensor) -> torch.Tensor:
         return x
 
+    def layernorm_unit_rows(self, x: torch.Tensor, norm) -> torch.Tensor:
+        return norm(x)          # reference :323; the L2 normalisation happens inside nn_field (util.py:66-67)
+
     def nn_field(self, x: torch.Tensor, piv: torch.Tensor, kf_a: Sequence[int], kf_b: Sequence[int]
                  ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
         F_, S, dim = x.shape

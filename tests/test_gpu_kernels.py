@@ -59,6 +59,26 @@ def test_unit_rows(ops, rows, dim):
     assert (got16.float() - want.float()).abs().max().item() < 2e-3
 
 
+@pytest.mark.parametrize("rows,dim", [(3, 8), (100, 40), (4096, 320), (2048, 640), (512, 1280)])
+def test_layernorm_unit_rows(ops, rows, dim):
+    """norm1 + row normalisation fused (frame pass): equals LayerNorm in fp32 followed by tf_unit_rows."""
+    torch.manual_seed(rows + dim)
+    norm = torch.nn.LayerNorm(dim).cuda().half()
+    with torch.no_grad():
+        norm.weight.uniform_(0.5, 1.5)
+        norm.bias.uniform_(-0.3, 0.3)
+    x = (torch.randn(rows, dim, device="cuda") * 2 + 0.3).half()
+    got = ops.layernorm_unit_rows(x, norm)
+    y = torch.nn.functional.layer_norm(x.float(), (dim,), norm.weight.float(), norm.bias.float(), norm.eps)
+    want = (y / y.norm(dim=-1, keepdim=True)).half()
+    assert got.dtype == torch.float16 and got.shape == x.shape
+    assert (got.float() - want.float()).abs().max().item() <= 1e-3
+    assert (got != want).float().mean().item() < 5e-3         # last-ulp rounding of the fp32 statistics only
+    # strided source-stream view (first third of a [3B, S, dim] tensor)
+    x3 = torch.cat([x, x * 2, x + 1]).view(3, rows, dim)
+    assert torch.equal(ops.layernorm_unit_rows(x3[0], norm), got)
+
+
 def test_unit_rows_empty(ops):
     assert ops.unit_rows(torch.empty(0, 64, device="cuda")).shape == (0, 64)
 

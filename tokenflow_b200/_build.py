@@ -32,6 +32,10 @@ NVCC_FLAGS = [
 ]
 
 
+if os.environ.get("TF_BUILD_TRACE"):          # debug build with the attention event trace compiled in
+    NVCC_FLAGS = NVCC_FLAGS + ["-DTF_TRACE"]
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):

@@ -117,6 +117,25 @@ int tf_unit_rows(const void* x, int x_is_f32, int64_t rows, int dim, int64_t x_r
   return e;
 }
 
+int tf_layernorm_unit_rows(const void* x_f16, int64_t rows, int dim, int64_t x_row_stride, const float* gamma,
+                           const float* beta, float eps, void* out_f16, tf_stream_t stream) {
+  if (rows < 0 || dim <= 0 || (dim & 7) || (x_row_stride & 7) || x_row_stride < dim) {
+    set_last_error("tf_layernorm_unit_rows: bad shape rows=%lld dim=%d stride=%lld (dim %% 8 == 0 required)",
+                   (long long)rows, dim, (long long)x_row_stride);
+    return TF_ERR_INVALID_ARGUMENT;
+  }
+  if (rows == 0) return TF_OK;
+  if (!x_f16 || !gamma || !beta || !out_f16 || !aligned16(x_f16) || !aligned16(out_f16) || !aligned16(gamma) ||
+      !aligned16(beta)) {
+    set_last_error("tf_layernorm_unit_rows: NULL or misaligned pointer");
+    return TF_ERR_INVALID_ARGUMENT;
+  }
+  int e = launch_layernorm_unit_rows(x_f16, rows, dim, x_row_stride, gamma, beta, eps, out_f16,
+                                     static_cast<cudaStream_t>(stream));
+  if (!e) g_launches += 1;
+  return e;
+}
+
 int tf_nn_field(const void* x_unit, const void* piv_unit, const int32_t* kf_a, const int32_t* kf_b, int F, int S,
                 int dim, int K, int32_t* idx_a, int32_t* idx_b, tf_stream_t stream) {
   if (S < 0 || dim <= 0 || (dim & 7) || K <= 0) {

@@ -245,6 +245,36 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
   return d;
 }
 
+// The same descriptor split in two 32-bit words, for issue loops that only advance the start address:
+//   lo = start address >> 4 | (LBO >> 4) << 16        hi = SBO >> 4 | version 1 | SWIZZLE_128B
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__host__ __device__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ void tc_mma_ss_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                             uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_ts_lh(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // Instruction descriptor for kind::f16 with fp16 operands and an fp32 accumulator.
 //   [4,6) D format (1 = f32)   [7,10) A format (0 = f16)   [10,13) B format (0 = f16)
 //   [15] A major (0 = K)       [16] B major (0 = K, 1 = MN)  [17,23) N >> 3   [24,29) M >> 4
@@ -260,6 +290,11 @@ __device__ __forceinline__ uint32_t pack_f16x2_rn(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // d = {hi: first src, lo: second src}
   return r;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {     // FMNMX3 (sm_100+): one instruction
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
 }
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;

@@ -37,7 +37,21 @@ namespace tf {
 namespace {
 
 constexpr int kBlockM = 128;
-constexpr float kRescaleThreshold = 8.0f;      // log2 units: P stays <= 2^8 without touching O
+constexpr float kRescaleThreshold = 8.0f;
+
+// Optional event trace (build with -DTF_TRACE): clock64 stamps of CTA 0's roles for the first tiles.
+// layout: g_attn_trace[role][tile][event], role 0/1 = softmax tile A/B (warp quadrant 0, lane 0), 2 = MMA issuer
+#ifdef TF_TRACE
+constexpr int kTraceTiles = 40, kTraceEvents = 8;
+__device__ long long g_attn_trace[3 * kTraceTiles * kTraceEvents];
+#define TF_TRACE_EV(role, tile, ev)                                                              \
+  do {                                                                                           \
+    if (blockIdx.x == 0 && (tile) < kTraceTiles)                                                 \
+      g_attn_trace[((role) * kTraceTiles + (tile)) * kTraceEvents + (ev)] = clock64();           \
+  } while (0)
+#else
+#define TF_TRACE_EV(role, tile, ev) do {} while (0)
+#endif      // log2 units: P stays <= 2^8 without touching O
 
 struct AttnCtl {
   uint64_t q_full;
@@ -53,6 +67,7 @@ struct AttnParams {
   int S, heads, d, n_out;
   int tiles_m;            // query tiles per (sample, head)
   int stages;
+  int handoff;            // ping-pong kernel: chunk index after which the MUFU token is handed over
   float scale_log2;       // scale * log2(e)
   long long out_tok_stride;   // elements between consecutive tokens of `out` (= heads*d)
 };
@@ -309,44 +324,56 @@ ext_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 
 
 // ================================================================================================
-// v2: two 128-query tiles per CTA ("ping-pong"), head dim <= 64.
+// Ping-pong kernel (head dim <= 64): two 128-query tiles per CTA, 64-key score tiles, every score
+// tile double-buffered in TMEM.
 //
-// The tensor pipe and the softmax warps alternate between the two query tiles, so S_B = Q_B K^T and
-// O_A += P_A V run while the other tile's warps are in their exp2 loop; K/V tiles are fetched once
-// for 256 queries.  Each softmax thread keeps its whole 128-column score row in registers (one TMEM
-// read per tile), and the row sum is not computed by the softmax warps at all: an extra N=16
-// tcgen05.mma against a constant tile of ones accumulates L = sum_k P[.,k] in TMEM from exactly the
-// fp16 probabilities that feed P V, so numerator and denominator stay consistent.
-//   warp 0: TMA   warp 1: MMA issue   warps 2-5: softmax tile A   warps 6-9: softmax tile B
-// TMEM: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) L_A [384,400) L_B [400,416)
+// The softmax inner loop is MUFU-bound on this chip (ex2: 8.1 cycles per warp instruction per SM
+// sub-partition, profiles/r01_pipe_throughput_ubench.txt; at d = 40 the two MMAs of a 128x128 tile
+// need only ~450 tensor cycles against ~1040 MUFU cycles), so the design goal is to keep two softmax
+// warps per sub-partition permanently busy:
+//   * two query tiles A and B (warps 2-5 / 6-9) share every K/V tile (fetched once per 256 queries);
+//   * S_X[t+2] = Q_X K_{t+2}^T is issued right after P_X[t] V_t, into the buffer P_X[t] just vacated,
+//     so a softmax warp never waits for the tensor pipe in steady state;
+//   * each softmax thread holds its 64-column score row in registers (one TMEM read per tile);
+//   * row sums come from an extra N=16 tcgen05.mma of P against a constant tile of ones, accumulated in
+//     TMEM from exactly the fp16 probabilities that feed P V (numerator and denominator consistent).
+//   warp 0: TMA   warps 1,2: MMA issue for tile A / B   warp 3: spare   warps 4-7: softmax A   warps 8-11: softmax B
+// TMEM: S_A[0] S_A[1] S_B[0] S_B[1] = 4 x 64 columns, O_A [256,320) O_B [320,384) L_A [384,400) L_B [400,416)
 // ================================================================================================
+constexpr int kPPStagesMax = 12;
 struct AttnCtl2 {
   uint64_t q_full;
-  uint64_t kv_full[8];
-  uint64_t kv_empty[8];
-  uint64_t s_full[2];
-  uint64_t p_full[2];
-  uint64_t pv_done[2];
+  uint64_t kv_full[kPPStagesMax];
+  uint64_t kv_empty[kPPStagesMax];
+  uint64_t s_full[2][2];
+  uint64_t p_full[2][2];
+  uint64_t xu_turn[2][4];    // [next tile X][SM sub-partition]: exp2-phase token passed between the two softmax
+                             // warps that share a sub-partition (and therefore its MUFU)
+  uint64_t pv_done[2][2];    // [tile X][t & 1]: two alternating barriers, so a softmax warp that runs two
+                             // tiles ahead of the tensor pipe can still name "P V of tile t" unambiguously
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(320, 1)
+// kBlockN = 128: one score buffer per query tile (S_X[t+1] is issued after P_X[t] V_t);
+// kBlockN =  64: two score buffers per query tile (S_X[t+2] is issued after P_X[t] V_t).
+template <int kBlockN>
+__global__ void __launch_bounds__(384, 1)
 ext_attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                    const __grid_constant__ CUtensorMap map_v, const AttnTable tab, const AttnParams prm,
                    __half* __restrict__ out) {
-  constexpr int kBlockN = 128;
+  constexpr int kNBuf = 128 / kBlockN;                // score buffers per query tile (TMEM columns [0,256) in total)
+  constexpr int kChunks = kBlockN / 32;
   constexpr int kQTileBytes = kBlockM * 128;          // one 128-query tile, 64-wide d chunk
   constexpr int kQBytes = 2 * kQTileBytes;
-  constexpr int kOnesBytes = 16 * 128;                // 16 key rows of ones (B operand of the row-sum MMA)
+  constexpr int kOnesBytes = 0;
   constexpr int kTileBytes = kBlockN * 128;
   constexpr int kStageBytes = 2 * kTileBytes;
-  constexpr int kOCol = 256, kLCol = 384;
+  constexpr int kOCol = 256;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* q_smem = smem;
-  uint8_t* ones_smem = smem + kQBytes;
-  uint8_t* ring = ones_smem + kOnesBytes;
+  uint8_t* ring = smem + kQBytes + kOnesBytes;
   AttnCtl2* ctl = reinterpret_cast<AttnCtl2*>(ring + prm.stages * kStageBytes);
 
   const int S = prm.S, d = prm.d, stages = prm.stages;
@@ -361,10 +388,7 @@ ext_attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   const int ksteps = (d + 15) / 16;
   const int n_pv = ((d + 15) / 16) * 16;
 
-  const int warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < kOnesBytes / 4; i += blockDim.x)
-    reinterpret_cast<uint32_t*>(ones_smem)[i] = 0x3C003C00u;   // fp16 1.0 pairs (layout/swizzle agnostic)
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&map_q);
     tma_prefetch_desc(&map_k);
@@ -372,12 +396,16 @@ ext_attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     mbar_init(&ctl->q_full, 1);
     for (int i = 0; i < stages; ++i) {
       mbar_init(&ctl->kv_full[i], 1);
-      mbar_init(&ctl->kv_empty[i], 1);
+      mbar_init(&ctl->kv_empty[i], 2);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&ctl->s_full[i], 1);
-      mbar_init(&ctl->p_full[i], 4);
-      mbar_init(&ctl->pv_done[i], 1);
+    for (int x = 0; x < 2; ++x) {
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&ctl->s_full[x][b], 1);
+        mbar_init(&ctl->p_full[x][b], 4);
+      }
+      mbar_init(&ctl->pv_done[x][0], 1);
+      mbar_init(&ctl->pv_done[x][1], 1);
+      for (int qd = 0; qd < 4; ++qd) mbar_init(&ctl->xu_turn[x][qd], 1);
     }
     fence_mbar_init();
   }
@@ -385,7 +413,7 @@ ext_attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = ctl->tmem_base;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);     // warp-uniform for the compiler
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -406,111 +434,126 @@ ext_attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         if (++stage == stages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 || warp == 2) {
+    // ===================== MMA issuers: one warp per query tile (warp 1 -> A, warp 2 -> B) ==============
+    // Measured (profiles/r01_ext_attn_trace.md): with one issuer serving both query tiles the issue path
+    // (8 small P V MMAs + 3 Q K^T MMAs + commits + barrier polls per tile and query tile) was the
+    // bottleneck and the softmax warps spent half their time waiting for the next score tile.  Two
+    // issuers run the two streams in parallel (all hazards — P_X[t] V before S_X[t+kNBuf] — are inside
+    // one stream).  Control flow and operands stay warp-uniform (the whole warp runs the loop, values
+    // derive from shfl-broadcast / kernel parameters) so that ptxas keeps descriptors in uniform
+    // registers and emits back-to-back UTCHMMA instead of an ELECT/R2UR loop around every MMA.
+    const int X = warp - 1;
     const uint32_t idesc_qk = umma_idesc_f16(128, kBlockN, 0);
     const uint32_t idesc_pv = umma_idesc_f16(128, (uint32_t)n_pv, 1);
-    const uint32_t idesc_l = umma_idesc_f16(128, 16, 1);
-    const uint32_t q_addr = smem_u32(q_smem);
-    const uint64_t ones_desc = umma_smem_desc(smem_u32(ones_smem), 16, 1024);
-    auto issue_qk = [&](int X, int stage) {       // S_X = Q_X K^T
-      const uint32_t k_addr = smem_u32(ring + stage * kStageBytes);
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const uint64_t da = umma_smem_desc(q_addr + X * kQTileBytes + ks * 32, 16, 1024);
-        const uint64_t db = umma_smem_desc(k_addr + ks * 32, 16, 1024);
-        tc_mma_ss(tmem_base + (uint32_t)(X * 128), da, db, idesc_qk, ks > 0 ? 1u : 0u);
-      }
-      tc_commit(&ctl->s_full[X]);
+    constexpr uint32_t hi_kmaj = umma_desc_hi(1024);
+    const uint32_t q_lo = umma_desc_lo(smem_u32(q_smem + X * kQTileBytes), 16);
+    const uint32_t ring_k_lo = umma_desc_lo(smem_u32(ring), 16);                       // K tile of stage 0
+    const uint32_t ring_v_lo = umma_desc_lo(smem_u32(ring + kTileBytes), kTileBytes);  // V tile of stage 0
+    constexpr uint32_t kStageStep = kStageBytes >> 4;
+    const uint32_t o_tmem = tmem_base + kOCol + X * 64;
+    // S_X[buf] = Q_X K^T against the K tile in ring stage `st` (called by the elected lane only)
+    auto issue_qk = [&](int st, int buf) {
+      const uint32_t k_lo = ring_k_lo + (uint32_t)st * kStageStep;
+      const uint32_t s_tmem = tmem_base + (uint32_t)((X * kNBuf + buf) * kBlockN);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)               // head dim <= 64: at most 4 k-steps of 16
+        if (ks < ksteps) tc_mma_ss_lh(s_tmem, q_lo + ks * 2, hi_kmaj, k_lo + ks * 2, hi_kmaj, idesc_qk, ks > 0 ? 1u : 0u);
+      tc_commit(&ctl->s_full[X][buf]);
     };
     mbar_wait(&ctl->q_full, 0);
-    mbar_wait(&ctl->kv_full[0], 0);
-    tc_fence_after_sync();
-    if (elect_one()) { issue_qk(0, 0); issue_qk(1, 0); }
-    __syncwarp();
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int t = 0; t < T; ++t) {
-      int nstage = stage + 1;
-      uint32_t nphase = phase;
-      if (nstage == stages) { nstage = 0; nphase ^= 1; }
-#pragma unroll
-      for (int X = 0; X < 2; ++X) {
-        mbar_wait(&ctl->p_full[X], (uint32_t)(t & 1));
-        tc_fence_after_sync();
-        if (elect_one()) {
-          const uint32_t v_addr = smem_u32(ring + stage * kStageBytes + kTileBytes);
-          const uint32_t p_tmem = tmem_base + (uint32_t)(X * 128);
-#pragma unroll
-          for (int k = 0; k < kBlockN / 16; ++k) {
-            const uint64_t db = umma_smem_desc(v_addr + k * (16 * 128), (uint32_t)kTileBytes, 1024);
-            const uint32_t acc = (t > 0 || k > 0) ? 1u : 0u;
-            tc_mma_ts(tmem_base + kOCol + X * 64, p_tmem + k * 8, db, idesc_pv, acc);
-            tc_mma_ts(tmem_base + kLCol + X * 16, p_tmem + k * 8, ones_desc, idesc_l, acc);
-          }
-          tc_commit(&ctl->pv_done[X]);
-          if (X == 1) tc_commit(&ctl->kv_empty[stage]);
-        }
-        __syncwarp();
-        if (t + 1 < T) {
-          if (X == 0) {
-            mbar_wait(&ctl->kv_full[nstage], nphase);
-            tc_fence_after_sync();
-          }
-          if (elect_one()) issue_qk(X, nstage);
-          __syncwarp();
-        }
-      }
-      stage = nstage;
-      phase = nphase;
+    // Tile B starts once tile A's first probabilities have arrived: that staggers the two softmax warps
+    // of every SM sub-partition by about half a period instead of letting them convoy.
+    if (X == 1) mbar_wait(&ctl->p_full[0][0], 0);
+    // ring position of the next K tile to be used by a Q K^T (tile t + kNBuf in the main loop)
+    int qk_stage = 0;
+    uint32_t qk_phase = 0;
+    for (int t0 = 0; t0 < kNBuf && t0 < T; ++t0) {
+      mbar_wait(&ctl->kv_full[qk_stage], qk_phase);
+      tc_fence_after_sync();
+      if (elect_one()) issue_qk(qk_stage, t0);
+      __syncwarp();
+      if (++qk_stage == stages) { qk_stage = 0; qk_phase ^= 1; }
     }
-  } else {
-    // ===================== softmax warps: tile X = (warp - 2) / 4 =====================
-    const int X = (warp - 2) >> 2;
+    int stage = 0;                                 // ring position of tile t (its V tile feeds P V)
+    for (int t = 0; t < T; ++t) {
+      const int buf = t % kNBuf;                   // kNBuf is 1 or 2
+      const bool refill = t + kNBuf < T;
+      if (refill) mbar_wait(&ctl->kv_full[qk_stage], qk_phase);   // K tile of the refill, polled while idle anyway
+      if (X == 0 && lane_id() == 0) TF_TRACE_EV(2, t, 0);
+      mbar_wait(&ctl->p_full[X][buf], (uint32_t)((t / kNBuf) & 1));
+      tc_fence_after_sync();
+      if (X == 0 && lane_id() == 0) TF_TRACE_EV(2, t, 1);
+      if (elect_one()) {
+        const uint32_t v_lo = ring_v_lo + (uint32_t)stage * kStageStep;
+        const uint32_t p_tmem = tmem_base + (uint32_t)((X * kNBuf + buf) * kBlockN);
+#pragma unroll
+        for (int k = 0; k < kBlockN / 16; ++k)      // O_X (+)= P_X[:, 16k:16k+16] V[16k:16k+16, :]
+          tc_mma_ts_lh(o_tmem, p_tmem + k * 8, v_lo + k * 128, hi_kmaj, idesc_pv, (t > 0 || k > 0) ? 1u : 0u);
+        tc_commit(&ctl->pv_done[X][t & 1]);
+        tc_commit(&ctl->kv_empty[stage]);          // count 2: the stage is free once both tiles' MMAs retired
+        if (refill) issue_qk(qk_stage, buf);        // refill the score buffer P_X[t] vacates
+      }
+      __syncwarp();
+      if (X == 0 && lane_id() == 0) TF_TRACE_EV(2, t, 3);
+      if (++stage == stages) stage = 0;
+      if (refill && ++qk_stage == stages) { qk_stage = 0; qk_phase ^= 1; }
+    }
+  } else if (warp >= 4) {              // (warp 3 is a spare: it keeps the softmax warps aligned to TMEM lane quadrants)
+    // ===================== softmax warps: tile X = (warp - 4) / 4 =====================
+    const int X = (warp - 4) >> 2;
     const int quad = warp & 3;
     const int row = quad * 32 + (int)lane_id();
     const uint32_t t_lane = (uint32_t)(quad * 32) << 16;
-    const uint32_t s_addr = tmem_base + t_lane + (uint32_t)(X * 128);
     const uint32_t o_addr = tmem_base + t_lane + kOCol + X * 64;
-    const uint32_t l_addr = tmem_base + t_lane + kLCol + X * 16;
     const float sl2 = prm.scale_log2;
     float m_run = 0.f;
+    float l_run = 0.f;       // row sum of the (unrounded) probabilities, same scale as O
+    int slab_tile = 0;
     for (int t = 0; t < T; ++t) {
-      const int slab_tile = t % tiles_per_slab;
       const int valid = min(kBlockN, S - slab_tile * kBlockN);
-      mbar_wait(&ctl->s_full[X], (uint32_t)(t & 1));
+      if (++slab_tile == tiles_per_slab) slab_tile = 0;
+      const uint32_t s_addr = tmem_base + t_lane + (uint32_t)((X * kNBuf + (t % kNBuf)) * kBlockN);
+      const bool tracer = (quad == 0 && lane_id() == 0);
+      if (tracer) TF_TRACE_EV(X, t, 0);
+      mbar_wait(&ctl->s_full[X][t % kNBuf], (uint32_t)((t / kNBuf) & 1));
       tc_fence_after_sync();
-      uint32_t v0[32], v1[32], v2[32], v3[32];
-      tmem_ld32(s_addr, v0);
-      tmem_ld32(s_addr + 32, v1);
-      tmem_ld32(s_addr + 64, v2);
-      tmem_ld32(s_addr + 96, v3);
+      if (tracer) TF_TRACE_EV(X, t, 1);
+      uint32_t v[kChunks][32];
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) tmem_ld32(s_addr + 32 * c, v[c]);
       tmem_wait_ld();
+      if (tracer) TF_TRACE_EV(X, t, 2);
       if (valid < kBlockN) {                       // ragged last tile of a keyframe: mask the padding keys
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (i >= valid) v0[i] = 0xFF800000u;
-          if (32 + i >= valid) v1[i] = 0xFF800000u;
-          if (64 + i >= valid) v2[i] = 0xFF800000u;
-          if (96 + i >= valid) v3[i] = 0xFF800000u;
-        }
-      }
-      float mt = -INFINITY;
+        for (int c = 0; c < kChunks; ++c)
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        mt = fmaxf(mt, fmaxf(fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])),
-                             fmaxf(__uint_as_float(v2[i]), __uint_as_float(v3[i]))));
+          for (int i = 0; i < 32; ++i)
+            if (32 * c + i >= valid) v[c][i] = 0xFF800000u;
       }
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};     // 4 independent FMNMX3 chains
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          mx[0] = fmax3(mx[0], __uint_as_float(v[c][i + 0]), __uint_as_float(v[c][i + 1]));
+          mx[1] = fmax3(mx[1], __uint_as_float(v[c][i + 2]), __uint_as_float(v[c][i + 3]));
+          mx[2] = fmax3(mx[2], __uint_as_float(v[c][i + 4]), __uint_as_float(v[c][i + 5]));
+          mx[3] = fmax3(mx[3], __uint_as_float(v[c][i + 6]), __uint_as_float(v[c][i + 7]));
+        }
+      const float mt = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
       const float mt_s = mt * sl2;
       if (t == 0) {
         m_run = mt_s;
       } else {
         const bool need = mt_s > m_run + kRescaleThreshold;
         if (__any_sync(0xffffffffu, need)) {
-          mbar_wait(&ctl->pv_done[X], (uint32_t)((t - 1) & 1));
+          mbar_wait(&ctl->pv_done[X][(t - 1) & 1], (uint32_t)(((t - 1) >> 1) & 1));   // P V of tile t-1 retired
           tc_fence_after_sync();
           const float m_new = fmaxf(m_run, mt_s);
           const float alpha = fast_exp2(m_run - m_new);
           m_run = m_new;
+          l_run *= alpha;
           for (int c0 = 0; c0 < n_pv; c0 += 16) {
             uint32_t o[16];
             tmem_ld16(o_addr + c0, o);
@@ -519,51 +562,49 @@ ext_attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
             tmem_st16(o_addr + c0, o);
           }
-          {
-            uint32_t o[16];
-            tmem_ld16(l_addr, o);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st16(l_addr, o);
-          }
           tmem_wait_st();
         }
       }
+      if (tracer) TF_TRACE_EV(X, t, 3);
+      // exp2 phase, MUFU-bound: the two warps of a sub-partition take turns (A t, B t, A t+1, ...) instead
+      // of running their exp2 loops concurrently at half speed each and then idling together while the
+      // tensor pipe produces their next score tiles (profiles/r01_ext_attn_trace.md).
+      if (X == 0) {
+        if (t > 0) mbar_wait(&ctl->xu_turn[0][quad], (uint32_t)((t - 1) & 1));
+      } else {
+        mbar_wait(&ctl->xu_turn[1][quad], (uint32_t)(t & 1));
+      }
       const float neg_m = -m_run;
-      uint32_t pk[16];
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int i = 0; i < 16; ++i)
-        pk[i] = pack_f16x2_rn(fast_exp2(fmaf(__uint_as_float(v0[2 * i]), sl2, neg_m)),
-                              fast_exp2(fmaf(__uint_as_float(v0[2 * i + 1]), sl2, neg_m)));
-      tmem_st16(s_addr, pk);
+      for (int c = 0; c < kChunks; ++c) {
+        uint32_t pk[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i)
-        pk[i] = pack_f16x2_rn(fast_exp2(fmaf(__uint_as_float(v1[2 * i]), sl2, neg_m)),
-                              fast_exp2(fmaf(__uint_as_float(v1[2 * i + 1]), sl2, neg_m)));
-      tmem_st16(s_addr + 16, pk);
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        pk[i] = pack_f16x2_rn(fast_exp2(fmaf(__uint_as_float(v2[2 * i]), sl2, neg_m)),
-                              fast_exp2(fmaf(__uint_as_float(v2[2 * i + 1]), sl2, neg_m)));
-      tmem_st16(s_addr + 32, pk);
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        pk[i] = pack_f16x2_rn(fast_exp2(fmaf(__uint_as_float(v3[2 * i]), sl2, neg_m)),
-                              fast_exp2(fmaf(__uint_as_float(v3[2 * i + 1]), sl2, neg_m)));
-      tmem_st16(s_addr + 48, pk);
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(v[c][2 * i]), sl2, neg_m));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(v[c][2 * i + 1]), sl2, neg_m));
+          ls[i & 3] += p0 + p1;
+          pk[i] = pack_f16x2_rn(p0, p1);
+        }
+        tmem_st16(s_addr + 16 * c, pk);
+        if (c == prm.handoff) {      // hand the MUFU over while the later chunks are still in flight: their tail
+          __syncwarp();              // (dependent FADD / F2FP / TMEM store latencies) overlaps the other warp's start
+          if (lane_id() == 0) mbar_arrive(&ctl->xu_turn[1 - X][quad]);
+        }
+      }
+      l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      if (tracer) TF_TRACE_EV(X, t, 4);
       tmem_wait_st();
+      if (tracer) TF_TRACE_EV(X, t, 5);
       tc_fence_before_sync();
       __syncwarp();
-      if (lane_id() == 0) mbar_arrive(&ctl->p_full[X]);
+      if (lane_id() == 0) mbar_arrive(&ctl->p_full[X][t % kNBuf]);
+      if (tracer) TF_TRACE_EV(X, t, 6);
     }
     // ---- final: O / L -> fp16 ----
-    mbar_wait(&ctl->pv_done[X], (uint32_t)((T - 1) & 1));
+    mbar_wait(&ctl->pv_done[X][(T - 1) & 1], (uint32_t)(((T - 1) >> 1) & 1));
     tc_fence_after_sync();
-    uint32_t lreg[16];
-    tmem_ld16(l_addr, lreg);
-    tmem_wait_ld();
-    const float inv_l = 1.0f / __uint_as_float(lreg[0]);
+    const float inv_l = 1.0f / l_run;
     const int p_tok = m0 + X * kBlockM + row;
     __half* orow = out + ((long long)smp.out_sample * S + p_tok) * prm.out_tok_stride + (long long)head * d;
     for (int c0 = 0; c0 < n_pv; c0 += 16) {
@@ -594,12 +635,13 @@ ext_attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   }
 }
 
+template <int kBlockN>
 int launch_pp(const void* q, const void* k, const void* v, long long q_tok_stride, long long kv_tok_stride,
               int q_samples_total, int kv_samples_total, const AttnTable& tab, int n_out, int S, int heads, int d,
               float scale, void* out, cudaStream_t stream) {
-  constexpr int kQBytes = 2 * kBlockM * 128, kOnesBytes = 16 * 128, kStageBytes = 2 * 128 * 128;
+  constexpr int kQBytes = 2 * kBlockM * 128, kOnesBytes = 0, kStageBytes = 2 * kBlockN * 128;
   int stages = (227 * 1024 - 2048 - kQBytes - kOnesBytes) / kStageBytes;
-  if (stages > 8) stages = 8;
+  if (stages > kPPStagesMax) stages = kPPStagesMax;
   const size_t smem_bytes = 1024 + kQBytes + kOnesBytes + (size_t)stages * kStageBytes + sizeof(AttnCtl2);
   CUtensorMap map_q, map_k, map_v;
   auto make = [&](CUtensorMap* m, const void* base, long long tok_stride, int samples, int box_rows) -> int {
@@ -612,20 +654,22 @@ int launch_pp(const void* q, const void* k, const void* v, long long q_tok_strid
     return TF_OK;
   };
   if (int e = make(&map_q, q, q_tok_stride, q_samples_total, kBlockM)) return e;
-  if (int e = make(&map_k, k, kv_tok_stride, kv_samples_total, 128)) return e;
-  if (int e = make(&map_v, v, kv_tok_stride, kv_samples_total, 128)) return e;
+  if (int e = make(&map_k, k, kv_tok_stride, kv_samples_total, kBlockN)) return e;
+  if (int e = make(&map_v, v, kv_tok_stride, kv_samples_total, kBlockN)) return e;
   AttnParams prm;
   prm.S = S; prm.heads = heads; prm.d = d; prm.n_out = n_out;
   prm.tiles_m = (S + 2 * kBlockM - 1) / (2 * kBlockM);
+  static const char* env_handoff = getenv("TF_EXT_ATTN_HANDOFF");     // tuning knob (profiling)
+  prm.handoff = env_handoff ? atoi(env_handoff) : (kBlockN / 32 - 2);
   prm.stages = stages;
   prm.scale_log2 = scale * 1.4426950408889634f;
   prm.out_tok_stride = (long long)heads * d;
-  if (check_cuda(cudaFuncSetAttribute(ext_attn_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes),
+  auto kern = ext_attn_pp_kernel<kBlockN>;
+  if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes),
                  "tf_ext_attn smem attribute"))
     return TF_ERR_CUDA;
   const long long grid = (long long)n_out * heads * prm.tiles_m;
-  ext_attn_pp_kernel<<<(unsigned)grid, 320, smem_bytes, stream>>>(map_q, map_k, map_v, tab, prm,
-                                                                 static_cast<__half*>(out));
+  kern<<<(unsigned)grid, 384, smem_bytes, stream>>>(map_q, map_k, map_v, tab, prm, static_cast<__half*>(out));
   return check_cuda(cudaGetLastError(), "tf_ext_attn launch");
 }
 
@@ -676,10 +720,16 @@ int launch_ext_attn(const void* q, const void* k, const void* v, long long q_tok
                     int q_samples_total, int kv_samples_total, const AttnTable& tab, int n_out, int S, int heads,
                     int d, float scale, void* out, cudaStream_t stream) {
   if (n_out == 0 || S == 0) return TF_OK;
-  static const bool force_v1 = getenv("TF_EXT_ATTN_V1") != nullptr;     // A/B switch for profiling
-  if (d <= 64 && S > 128 && !force_v1)
-    return launch_pp(q, k, v, q_tok_stride, kv_tok_stride, q_samples_total, kv_samples_total, tab, n_out, S, heads,
-                     d, scale, out, stream);
+  // A/B switch for profiling: TF_EXT_ATTN_MODE = v1 (one query tile per CTA) | pp128 | pp64
+  static const char* mode = getenv("TF_EXT_ATTN_MODE");
+  const bool force_v1 = mode && mode[0] == 'v';
+  if (d <= 64 && S > 128 && !force_v1) {
+    if (mode && mode[2] == '6')
+      return launch_pp<64>(q, k, v, q_tok_stride, kv_tok_stride, q_samples_total, kv_samples_total, tab, n_out, S,
+                           heads, d, scale, out, stream);
+    return launch_pp<128>(q, k, v, q_tok_stride, kv_tok_stride, q_samples_total, kv_samples_total, tab, n_out, S,
+                          heads, d, scale, out, stream);
+  }
   if (d <= 64)
     return launch_cfg<1, 128>(q, k, v, q_tok_stride, kv_tok_stride, q_samples_total, kv_samples_total, tab, n_out,
                               S, heads, d, scale, out, stream);
@@ -693,4 +743,16 @@ int launch_ext_attn(const void* q, const void* k, const void* v, long long q_tok
   return TF_ERR_UNSUPPORTED;
 }
 
+#ifdef TF_TRACE
+int read_attn_trace(long long* host, int n) {
+  const int total = 3 * kTraceTiles * kTraceEvents;
+  if (n > total) n = total;
+  return check_cuda(cudaMemcpyFromSymbol(host, g_attn_trace, sizeof(long long) * n), "trace read");
+}
+#endif
+
 }  // namespace tf
+
+#ifdef TF_TRACE
+extern "C" int tf_debug_read_attn_trace(long long* host, int n) { return tf::read_attn_trace(host, n); }
+#endif

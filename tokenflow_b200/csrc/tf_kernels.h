@@ -19,6 +19,9 @@ struct FrameTable {
 int launch_unit_rows(const void* x, int x_is_f32, long long rows, int dim, long long row_stride, void* out_f16,
                      cudaStream_t stream);
 
+int launch_layernorm_unit_rows(const void* x_f16, long long rows, int dim, long long row_stride, const float* gamma,
+                               const float* beta, float eps, void* out_f16, cudaStream_t stream);
+
 int launch_propagate(const void* A, const int32_t* idx_a, const int32_t* idx_b, const FrameTable& tab, int F,
                      int S, int dim, int K, const void* residual, void* out, int out_is_f32,
                      cudaStream_t stream);

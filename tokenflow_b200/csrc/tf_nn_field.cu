@@ -20,6 +20,8 @@
 //
 // Roofline: tensor-bound, 2*rows*S*dim flops per (frame, keyframe) pair; HBM traffic is only the
 // operands (a few MB, L2 resident) and the int32 indices.
+#include <cstdlib>
+
 #include "tf_common.cuh"
 #include "tf_kernels.h"
 
@@ -140,46 +142,43 @@ nn_field_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    int stage = 0;
-    uint32_t phase = 0;
-    uint32_t it = 0;
-    uint32_t tile_ctr = 0;                       // accumulator tiles issued so far (buffer = ctr & 1)
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      if (kResidentA) {
-        mbar_wait(&ctl->a_full, it & 1);
-        tc_fence_after_sync();
-      }
-      for (int nt = 0; nt < n_tiles; ++nt, ++tile_ctr) {
-        const uint32_t acc = tile_ctr & 1;
-        mbar_wait(&ctl->tmem_empty[acc], ((tile_ctr >> 1) & 1) ^ 1);
-        tc_fence_after_sync();
-        for (int kc = 0; kc < nkc; ++kc) {
-          mbar_wait(&ctl->full[stage], phase);
+    // ===================== MMA issuer: one thread, descriptors advanced by 32-bit adds =====================
+    if (lane_id() == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0;
+      uint32_t tile_ctr = 0;                       // accumulator tiles issued so far (buffer = ctr & 1)
+      constexpr uint32_t hi = umma_desc_hi(1024);
+      const uint32_t ring_lo = umma_desc_lo(smem_u32(ring), 16);
+      const uint32_t a_res_lo = umma_desc_lo(smem_u32(a_res), 16);
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        if (kResidentA) {
+          mbar_wait(&ctl->a_full, it & 1);
           tc_fence_after_sync();
-          if (elect_one()) {
-            const uint8_t* st = ring + stage * kStageBytes;
-            const uint32_t b_addr = smem_u32(st);
-            const uint32_t a_addr = kResidentA ? smem_u32(a_res + kc * kAChunkBytes) : smem_u32(st + kBChunkBytes);
+        }
+        for (int nt = 0; nt < n_tiles; ++nt, ++tile_ctr) {
+          const uint32_t acc = tile_ctr & 1;
+          mbar_wait(&ctl->tmem_empty[acc], ((tile_ctr >> 1) & 1) ^ 1);
+          tc_fence_after_sync();
+          const uint32_t d_tmem = tmem_base + acc * kAccCols;
+          for (int kc = 0; kc < nkc; ++kc) {
+            mbar_wait(&ctl->full[stage], phase);
+            tc_fence_after_sync();
+            const uint32_t b_lo = ring_lo + (uint32_t)stage * (kStageBytes >> 4);
+            const uint32_t a_lo = kResidentA ? a_res_lo + (uint32_t)kc * (kAChunkBytes >> 4) : b_lo + (kBChunkBytes >> 4);
 #pragma unroll
             for (int h = 0; h < kHalves; ++h) {
 #pragma unroll
-              for (int k4 = 0; k4 < kChunkK / 16; ++k4) {
-                const uint64_t da = umma_smem_desc(a_addr + h * (128 * 128) + k4 * 32, 16, 1024);
-                const uint64_t db = umma_smem_desc(b_addr + k4 * 32, 16, 1024);
-                tc_mma_ss(tmem_base + acc * kAccCols + h * kBlockN, da, db, kIdesc, (kc > 0 || k4 > 0) ? 1u : 0u);
-              }
+              for (int k4 = 0; k4 < kChunkK / 16; ++k4)
+                tc_mma_ss_lh(d_tmem + h * kBlockN, a_lo + h * ((128 * 128) >> 4) + k4 * 2, hi, b_lo + k4 * 2, hi, kIdesc,
+                             (kc > 0 || k4 > 0) ? 1u : 0u);
             }
             tc_commit(&ctl->empty[stage]);                 // smem stage reusable once these MMAs retire
             if (kc == nkc - 1) tc_commit(&ctl->tmem_full[acc]);
+            if (++stage == stages) { stage = 0; phase ^= 1; }
           }
-          __syncwarp();
-          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
-      }
-      if (kResidentA) {
-        if (elect_one()) tc_commit(&ctl->a_empty);           // A tile free once the item's MMAs retire
-        __syncwarp();
+        if (kResidentA) tc_commit(&ctl->a_empty);           // A tile free once the item's MMAs retire
       }
     }
   } else {
@@ -308,6 +307,8 @@ int launch_nn_field(const void* x_unit, const void* piv_unit, const FrameTable& 
                     int32_t* idx_a, int32_t* idx_b, cudaStream_t stream) {
   if (F == 0 || S == 0) return TF_OK;
   int cfg = g_nn_field_force_cfg;
+  static const char* env_cfg = getenv("TF_NN_FIELD_CFG");           // A/B switch for profiling
+  if (cfg < 0 && env_cfg) cfg = env_cfg[0] - '0';
   if (cfg < 0) cfg = (dim <= 320 && S >= 256) ? 0 : (dim <= 640 ? 1 : 2);
   const int block_m = (cfg == 0) ? 256 : 128;
   NNItems items;

@@ -90,3 +90,121 @@ int launch_unit_rows(const void* x, int x_is_f32, long long rows, int dim, long 
 }
 
 }  // namespace tf
+
+// ------------------------------------------------------------------------------------------------
+// tf_layernorm_unit_rows — norm1 (LayerNorm) fused with the row L2-normalisation, for the frame pass.
+//
+// In the frame pass the reference evaluates norm1 on all three streams (tokenflow_utils.py:323) but
+// only the source stream's output is ever used, and only as the NN-field query (:335): attn1 is
+// skipped.  This kernel therefore reads the source third of `hidden_states` (fp16) once and writes the
+// fp16 unit rows directly:   y = LN(x) in fp32 (autocast runs layer_norm in fp32: mean / biased
+// variance / eps inside the rsqrt / affine),  out = fp16(y / ||y||_2)  — the same arithmetic as
+// norm1 followed by tf_unit_rows, without materialising the fp32 [3B,S,dim] tensor or touching the
+// uncond/cond streams.  One warp per row, whole row held in registers (dim <= 1280).
+// ------------------------------------------------------------------------------------------------
+namespace tf {
+namespace {
+
+constexpr int kLnMaxVecPerLane = 5;     // 5 x 8 halves x 32 lanes = 1280 channels
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+layernorm_unit_rows_kernel(const __half* __restrict__ x, long long rows, int dim, long long row_stride,
+                           const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                           __half* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int nvec = dim >> 3;
+  const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
+  const float inv_dim = 1.0f / (float)dim;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    const __half* xr = x + r * row_stride;
+    float v[kLnMaxVecPerLane][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < kLnMaxVecPerLane; ++j) {
+      const int vi = lane + 32 * j;
+      if (vi < nvec) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(xr + vi * 8);
+        const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h[e]);
+          v[j][2 * e] = f.x;
+          v[j][2 * e + 1] = f.y;
+          sum += f.x + f.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * inv_dim;
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < kLnMaxVecPerLane; ++j) {
+      if (lane + 32 * j < nvec) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float dlt = v[j][e] - mean;
+          sq += dlt * dlt;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * inv_dim + eps);
+    double ss = 0.0;
+#pragma unroll
+    for (int j = 0; j < kLnMaxVecPerLane; ++j) {
+      const int vi = lane + 32 * j;
+      if (vi < nvec) {
+        const float4 g0 = *reinterpret_cast<const float4*>(gamma + vi * 8);
+        const float4 g1 = *reinterpret_cast<const float4*>(gamma + vi * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(beta + vi * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(beta + vi * 8 + 4);
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float y = (v[j][e] - mean) * rstd * g[e] + b[e];
+          v[j][e] = y;
+          ss += (double)y * y;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float nrm = (float)sqrt(ss);
+    __half* orow = out + r * dim;
+#pragma unroll
+    for (int j = 0; j < kLnMaxVecPerLane; ++j) {
+      const int vi = lane + 32 * j;
+      if (vi < nvec) {
+        uint4 w;
+        __half2* h = reinterpret_cast<__half2*>(&w);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          h[e] = __floats2half2_rn(__fdiv_rn(v[j][2 * e], nrm), __fdiv_rn(v[j][2 * e + 1], nrm));
+        *reinterpret_cast<uint4*>(orow + vi * 8) = w;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+int launch_layernorm_unit_rows(const void* x_f16, long long rows, int dim, long long row_stride, const float* gamma,
+                               const float* beta, float eps, void* out_f16, cudaStream_t stream) {
+  if (rows == 0) return TF_OK;
+  if ((dim >> 3) > 32 * kLnMaxVecPerLane) {
+    set_last_error("tf_layernorm_unit_rows: dim=%d > %d is not supported", dim, 8 * 32 * kLnMaxVecPerLane);
+    return TF_ERR_UNSUPPORTED;
+  }
+  long long blocks = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const long long cap = (long long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  layernorm_unit_rows_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, stream>>>(
+      static_cast<const __half*>(x_f16), rows, dim, row_stride, gamma, beta, eps, static_cast<__half*>(out_f16));
+  return check_cuda(cudaGetLastError(), "tf_layernorm_unit_rows launch");
+}
+
+}  // namespace tf

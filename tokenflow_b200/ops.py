@@ -30,6 +30,9 @@ _SIGNATURES = {
     "tf_launch_count": (ctypes.c_int64, []),
     "tf_unit_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int64,
                                     ctypes.c_void_p, ctypes.c_void_p]),
+    "tf_layernorm_unit_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int64,
+                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p,
+                                              ctypes.c_void_p]),
     "tf_nn_field": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _c_i32p, _c_i32p, ctypes.c_int, ctypes.c_int,
                                    ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "tf_propagate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _c_i32p, _c_i32p, _c_f32p,
@@ -180,6 +183,26 @@ class CudaOps:
         self._timed("tf_unit_rows", nbytes, lambda: self._check(
             self.lib.tf_unit_rows(x2.data_ptr(), int(x2.dtype == torch.float32), x2.shape[0], dim,
                                   x2.stride(0), out.data_ptr(), self._stream()), "tf_unit_rows"))
+        return out.view(*x.shape)
+
+    def layernorm_unit_rows(self, x: torch.Tensor, norm: torch.nn.LayerNorm) -> torch.Tensor:
+        """fp16 [..., dim] → fp16 unit rows of LayerNorm(x) (fp32 statistics): norm1 + unit_rows in one
+        pass over the source stream (reference tokenflow_utils.py:323 + util.py:66-67)."""
+        dim = x.shape[-1]
+        if x.dtype != torch.float16 or dim > 1280 or norm.weight is None or norm.bias is None:
+            return self.unit_rows(norm(x))                       # shapes the fused kernel does not cover
+        cache = norm.__dict__.get("_tf_affine_f32")
+        if cache is None or cache[0] is not norm.weight or cache[1].device != x.device:
+            cache = (norm.weight, norm.weight.detach().float().contiguous(), norm.bias.detach().float().contiguous())
+            norm.__dict__["_tf_affine_f32"] = cache
+        x2 = x.reshape(-1, dim)
+        if x2.stride(-1) != 1 or x2.stride(0) % 8:
+            x2 = x2.contiguous()
+        out = torch.empty(x2.shape, dtype=torch.float16, device=x.device)
+        self._timed("tf_layernorm_unit_rows", x2.shape[0] * dim * 4, lambda: self._check(
+            self.lib.tf_layernorm_unit_rows(x2.data_ptr(), x2.shape[0], dim, x2.stride(0), cache[1].data_ptr(),
+                                            cache[2].data_ptr(), float(norm.eps), out.data_ptr(), self._stream()),
+            "tf_layernorm_unit_rows"))
         return out.view(*x.shape)
 
     def nn_field(self, x_unit: torch.Tensor, piv_unit: torch.Tensor, kf_a: Sequence[int],

@@ -345,8 +345,9 @@ def make_tokenflow_attention_block(block_class: Type[torch.nn.Module]) -> Type[t
             batch_size, sequence_length, dim = hidden_states.shape
             n_frames = batch_size // 3
             ops = _ops()
-            norm_hidden_states = self.norm1(hidden_states)
             cross_attention_kwargs = cross_attention_kwargs if cross_attention_kwargs is not None else {}
+            if self.pivotal_pass:
+                norm_hidden_states = self.norm1(hidden_states)
 
             shard = getattr(self, "_tf_shard", None)
             if self.pivotal_pass and shard is not None:
@@ -376,7 +377,8 @@ def make_tokenflow_attention_block(block_class: Type[torch.nn.Module]) -> Type[t
                     raise ValueError(f"frame table has {len(kf_a)} entries but the pass has {n_frames} frames")
                 kf = self.kf_attn_output
                 n_kf = kf.shape[0] // 3
-                x_unit = ops.unit_rows(norm_hidden_states[:n_frames])                    # source stream only (:335)
+                # norm1 of the source stream only — the other two thirds are never used in this branch (:335)
+                x_unit = ops.layernorm_unit_rows(hidden_states[:n_frames], self.norm1)
                 idx_a, idx_b = ops.nn_field(x_unit, self._tf_pivot_unit, kf_a, kf_b)      # :335-343
                 out_dtype = torch.float32 if (_strict_dtype() and idx_b is not None) else None
                 hidden_states = ops.propagate(kf.view(3, n_kf, sequence_length, dim), idx_a, idx_b, kf_a, kf_b, w,

@@ -1,0 +1,15 @@
+#!/bin/bash
+mkdir -p gpurun_out; rm -f gpurun_out/r10.log
+for mode in pp128 pp64; do
+  echo "=== attn mode $mode" >> gpurun_out/r10.log
+  TF_EXT_ATTN_MODE=$mode timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -p no:cacheprovider --timeout 180 -k "ext_attn" 2>&1 | tail -3 >> gpurun_out/r10.log
+  TF_EXT_ATTN_MODE=$mode timeout 300 python tools/kbench.py 2>&1 | grep -E "ext_attn_S4096|sdpa_S4096" >> gpurun_out/r10.log
+done
+for cfg in 0 1; do
+  echo "=== nn cfg $cfg" >> gpurun_out/r10.log
+  TF_NN_FIELD_CFG=$cfg timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -p no:cacheprovider --timeout 180 -k "nn_field" 2>&1 | tail -3 >> gpurun_out/r10.log
+  TF_NN_FIELD_CFG=$cfg timeout 300 python tools/kbench.py 2>&1 | grep -E "^nn_field" >> gpurun_out/r10.log
+done
+TF_BUILD_TRACE=1 python -m tokenflow_b200._build --force > /dev/null 2>&1
+TF_EXT_ATTN_MODE=pp128 timeout 120 python tools/trace_attn.py 2>&1 | tail -40 > gpurun_out/trace2.log
+cat gpurun_out/r10.log; head -14 gpurun_out/trace2.log; tail -6 gpurun_out/trace2.log

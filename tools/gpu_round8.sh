@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out; rm -f gpurun_out/r8.log
+for mode in pp128 pp64; do
+  echo "=== mode $mode" >> gpurun_out/r8.log
+  TF_EXT_ATTN_MODE=$mode timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -p no:cacheprovider --timeout 180 -k "ext_attn or nn_field" 2>&1 | tail -4 >> gpurun_out/r8.log
+  TF_EXT_ATTN_MODE=$mode timeout 300 python tools/kbench.py 2>&1 | grep -E "ext_attn_S4096|sdpa_S4096|^nn_field|^ext_attn_S1024" >> gpurun_out/r8.log
+done
+cat gpurun_out/r8.log

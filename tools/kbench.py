@@ -18,7 +18,8 @@ def timed(fn, iters=10, warmup=3, flush=None):
     ts = []
     for _ in range(iters):
         if flush is not None:
-            flush.zero_()
+            flush.zero_()                 # write > L2 capacity ...
+            flush[:: 64].sum()            # ... then touch it read-only so no dirty lines are evicted mid-measurement
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         fn()

@@ -21,7 +21,22 @@ __global__ void k(float* out, float seed) {
       if (MODE == 1) asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(h[i]));
       if (MODE == 2) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(seed), "f"(a[(i + 1) % UNROLL]));
       if (MODE == 3) asm volatile("max.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(a[(i + 1) % UNROLL]));
-      if (MODE == 4) asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(a[i]), "f"(a[(i + 1) % UNROLL]));
+      if (MODE == 4) {   // keep the conversion live: its result feeds the next iteration's input
+        unsigned t;
+        asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(t) : "f"(a[i]), "f"(a[(i + 1) % UNROLL]));
+        a[i] = __uint_as_float(t | 0x3f000000u);
+      }
+      if (MODE == 10) asm volatile("ex2.approx.f32 %0, %0;" : "+f"(a[i]));          // non-ftz MUFU
+      if (MODE == 11) {  // integer fp32->fp16 pack (round-half-up) : 2 IADD + 2 SHF + 1 LOP3 per pair
+        unsigned x0 = __float_as_uint(a[i]) + 0x1000u, x1 = __float_as_uint(a[(i + 1) % UNROLL]) + 0x1000u;
+        unsigned t = ((x1 << 3) & 0xFFFF0000u) | (x0 >> 13);
+        a[i] = __uint_as_float(t | 0x3f000000u);
+      }
+      if (MODE == 12) {  // scalar cvt.rn.f16.f32 (F2F)
+        unsigned short t;
+        asm volatile("cvt.rn.f16.f32 %0, %1;" : "=h"(t) : "f"(a[i]));
+        a[i] = __uint_as_float((unsigned)t | 0x3f000000u);
+      }
       if (MODE == 5) asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(h[i]) : "r"(h[(i + 1) % UNROLL]), "r"(h[(i + 2) % UNROLL]));
       if (MODE == 6) asm volatile("max.f16x2 %0, %0, %1;" : "+r"(h[i]) : "r"(h[(i + 1) % UNROLL]));
       if (MODE == 7) asm volatile("add.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(a[(i + 1) % UNROLL]));
@@ -77,6 +92,9 @@ int main() {
     run<7>("FADD", w, 1);
     run<8>("poly exp2 (per exp)", w, 1);
     run<9>("mix ex2+ffma+max+add (x4)", w, 4);
+    run<10>("MUFU.EX2 f32 non-ftz", w, 1);
+    run<11>("int pack f32x2->f16x2 (5 ALU)", w, 1);
+    run<12>("cvt.rn.f16.f32 scalar", w, 1);
   }
   return 0;
 }
