@@ -186,3 +186,19 @@ def test_load_source_latents(tmp_path):
     assert torch.equal(tfu.load_source_latents_t(torch.tensor(961), lat), src[961])
     with pytest.raises(AssertionError):
         tfu.load_source_latents_t(1, lat)
+
+
+def test_frames_per_pass_equals_reference_schedule(golden_dir):
+    """All frames in one frame pass (per-frame keyframe table) == the reference's per-batch passes."""
+    tfu._install_ops_for_testing(OracleOps())
+    c = _load(golden_dir, "unet_c1_pnp.pt")
+    cfg = dict(c["config"], frames_per_pass=cfg_frames if (cfg_frames := c["config"]["n_frames"]) else 4)
+    unet = sd_unet.build_unet("tiny", seed=c["seed"])
+    x, text, pnp, src = synthetic_inputs(cfg["n_frames"], c["latent"], unet.config.cross_attention_dim,
+                                         cfg["n_timesteps"], seed=c["seed"], ctx_len=c["ctx_len"])
+    ed = TokenFlowEditor(unet, DDIMScheduler(), tfu, cfg, text, pnp, source_latents=lambda t: src[t])
+    ed.init_method()
+    torch.manual_seed(c["seed"])
+    out = ed.sample_loop(x)
+    assert ed.keyframe_log == c["keyframes"]
+    assert torch.allclose(out, c["out"], atol=2e-4, rtol=1e-4)

@@ -8,7 +8,8 @@
 // config, written once and re-read twice by the reference) never exists: it lives 128xN tiles at
 // a time in tensor memory and is consumed by a running (max, first-argmax) epilogue.
 //
-// Kernel shape (one persistent CTA per SM, static round-robin over work items):
+// Kernel shape (one persistent CTA per SM, static round-robin over work items; default kHalves = 1,
+// kBlockN = 256 — see launch_nn_field for the measured choice):
 //   work item   = (frame f, tile of kHalves*128 tokens, keyframe kf)           -> 128*kHalves indices
 //   warp 0      = TMA producer: the item's A tile (tokens x dim, resident for the whole N sweep when
 //                 it fits) and a kStages-deep ring of B tiles (kBlockN keyframe tokens x 64 channels)
@@ -308,8 +309,15 @@ int launch_nn_field(const void* x_unit, const void* piv_unit, const FrameTable& 
   if (F == 0 || S == 0) return TF_OK;
   int cfg = g_nn_field_force_cfg;
   static const char* env_cfg = getenv("TF_NN_FIELD_CFG");           // A/B switch for profiling
-  if (cfg < 0 && env_cfg) cfg = env_cfg[0] - '0';
-  if (cfg < 0) cfg = (dim <= 320 && S >= 256) ? 0 : (dim <= 640 ? 1 : 2);
+  if (cfg < 0 && env_cfg) {
+    cfg = env_cfg[0] - '0';
+    if (cfg == 0 && dim > 320) cfg = 1;          // a forced configuration only applies where it fits
+    if (cfg == 1 && dim > 640) cfg = 2;
+  }
+  // Default: 128-token tiles with N = 256 MMAs.  Measured at the C2 top level (profiles/r01_kbench.json):
+  // <1,256> 1157 TFLOP/s vs <2,128> 959 — a tcgen05.mma costs ~90-100 cycles to issue whatever its shape,
+  // so the 64-cycle N = 128 MMAs of the 256-token configuration leave the tensor pipe a third idle.
+  if (cfg < 0) cfg = dim <= 640 ? 1 : 2;
   const int block_m = (cfg == 0) ? 256 : 128;
   NNItems items;
   items.tiles_per_frame = (S + block_m - 1) / block_m;

@@ -109,10 +109,20 @@ class TokenFlowEditor(nn.Module):
             h.register_pivotal(self, True)
             self.denoise_step(x[pivotal_idx], t, indices[pivotal_idx])
             h.register_pivotal(self, False)
+            per_pass = int(self.config.get("frames_per_pass", batch_size))
+            if per_pass == batch_size:                                   # the reference's schedule (:229-231)
+                denoised = []
+                for i, b in enumerate(range(0, len(x), batch_size)):
+                    h.register_batch_idx(self, i)
+                    denoised.append(self.denoise_step(x[b:b + batch_size], t, indices[b:b + batch_size]))
+                return torch.cat(denoised)
+            # same arithmetic, fewer and larger UNet passes: frames of several batches in one pass, each frame
+            # carrying its own (keyframe, previous keyframe, weight) — the per-frame table the kernels take
             denoised = []
-            for i, b in enumerate(range(0, len(x), batch_size)):
-                h.register_batch_idx(self, i)
-                denoised.append(self.denoise_step(x[b:b + batch_size], t, indices[b:b + batch_size]))
+            for b in range(0, len(x), per_pass):
+                frames = list(range(b, min(len(x), b + per_pass)))
+                h.register_frame_table(self, *self.frame_table(frames))
+                denoised.append(self.denoise_step(x[b:b + per_pass], t, indices[b:b + per_pass]))
             return torch.cat(denoised)
 
     # ------------------------------------------------------------------------------------
