@@ -576,17 +576,26 @@ ext_attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       }
       const float neg_m = -m_run;
       float ls[4] = {0.f, 0.f, 0.f, 0.f};
+      // Software-pipelined by hand: the exp2 of chunk c are issued interleaved with the row-sum / fp16 pack /
+      // TMEM store of chunk c-1, so every consumer sits >= 32 instructions behind its MUFU.EX2 and one warp
+      // alone keeps the MUFU pipe streaming (ptxas otherwise schedules "MUFU, MUFU, FADD of those two",
+      // which stalls on the MUFU latency after every pair: profiles/r01_ext_attn_trace.md).
 #pragma unroll
-      for (int c = 0; c < kChunks; ++c) {
+      for (int c = 0; c <= kChunks; ++c) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(v[c][2 * i]), sl2, neg_m));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(v[c][2 * i + 1]), sl2, neg_m));
-          ls[i & 3] += p0 + p1;
-          pk[i] = pack_f16x2_rn(p0, p1);
+          if (c < kChunks) {
+            v[c][2 * i] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(v[c][2 * i]), sl2, neg_m)));
+            v[c][2 * i + 1] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(v[c][2 * i + 1]), sl2, neg_m)));
+          }
+          if (c > 0) {
+            const float p0 = __uint_as_float(v[c - 1][2 * i]), p1 = __uint_as_float(v[c - 1][2 * i + 1]);
+            ls[i & 3] += p0 + p1;
+            pk[i] = pack_f16x2_rn(p0, p1);
+          }
         }
-        tmem_st16(s_addr + 16 * c, pk);
+        if (c > 0) tmem_st16(s_addr + 16 * (c - 1), pk);
         if (c == prm.handoff) {      // hand the MUFU over while the later chunks are still in flight: their tail
           __syncwarp();              // (dependent FADD / F2FP / TMEM store latencies) overlaps the other warp's start
           if (lane_id() == 0) mbar_arrive(&ctl->xu_turn[1 - X][quad]);

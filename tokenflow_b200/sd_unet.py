@@ -56,6 +56,29 @@ def tiny_config(ctx: int = 32) -> UNetConfig:
                       num_heads=(2, 2, 4, 4), norm_num_groups=8, sample_size=16)
 
 
+class GroupNorm(nn.GroupNorm):
+    """GroupNorm that stays in fp16 when fed fp16 under autocast (fp32 statistics inside the kernel).
+    Autocast's default policy would up-cast the input, write an fp32 output and let the next conv cast
+    it back — three extra full-tensor passes per norm that dominated the UNet body's time."""
+
+    def forward(self, x):
+        if x.dtype == torch.float16 and x.is_cuda and torch.is_autocast_enabled():
+            with torch.autocast("cuda", enabled=False):
+                return F.group_norm(x, self.num_groups, self.weight, self.bias, self.eps)
+        return super().forward(x)
+
+
+class BodyLayerNorm(nn.LayerNorm):
+    """Same for norm2 / norm3 of the transformer blocks.  (norm1 stays a plain nn.LayerNorm: its fp32
+    autocast output is part of the reference's NN-field arithmetic.)"""
+
+    def forward(self, x):
+        if x.dtype == torch.float16 and x.is_cuda and torch.is_autocast_enabled():
+            with torch.autocast("cuda", enabled=False):
+                return F.layer_norm(x, self.normalized_shape, self.weight, self.bias, self.eps)
+        return super().forward(x)
+
+
 class UNetOutput(dict):
     """`unet(...)['sample']` (reference run_tokenflow_pnp.py:210) and `.sample` both work."""
 
@@ -109,8 +132,11 @@ class GEGLU(nn.Module):
         self.proj = nn.Linear(dim_in, dim_out * 2)
 
     def forward(self, x):
-        x, gate = self.proj(x).chunk(2, dim=-1)
-        return x * F.gelu(gate)
+        # two GEMMs on the two halves of the fused weight: both outputs contiguous, so gelu and the
+        # product run vectorised (chunking one fused output leaves strided views and the slow path)
+        w_x, w_g = self.proj.weight.chunk(2, dim=0)
+        b_x, b_g = self.proj.bias.chunk(2, dim=0)
+        return F.linear(x, w_x, b_x) * F.gelu(F.linear(x, w_g, b_g))
 
 
 class FeedForward(nn.Module):
@@ -134,9 +160,9 @@ class BasicTransformerBlock(nn.Module):
         self.use_ada_layer_norm_zero = False
         self.norm1 = nn.LayerNorm(dim)
         self.attn1 = Attention(dim, None, heads, dim_head)
-        self.norm2 = nn.LayerNorm(dim)
+        self.norm2 = BodyLayerNorm(dim)
         self.attn2 = Attention(dim, cross_attention_dim, heads, dim_head)
-        self.norm3 = nn.LayerNorm(dim)
+        self.norm3 = BodyLayerNorm(dim)
         self.ff = FeedForward(dim)
 
     def forward(self, hidden_states, attention_mask=None, encoder_hidden_states=None,
@@ -153,7 +179,7 @@ class Transformer2DModel(nn.Module):
     def __init__(self, channels: int, heads: int, cross_attention_dim: int, groups: int, linear_proj: bool):
         super().__init__()
         self.use_linear_projection = linear_proj
-        self.norm = nn.GroupNorm(groups, channels, eps=1e-6)
+        self.norm = GroupNorm(groups, channels, eps=1e-6)
         if linear_proj:
             self.proj_in = nn.Linear(channels, channels)
             self.proj_out = nn.Linear(channels, channels)
@@ -193,10 +219,10 @@ class ResnetBlock2D(nn.Module):
 
     def __init__(self, in_channels: int, out_channels: int, temb_channels: int, groups: int):
         super().__init__()
-        self.norm1 = nn.GroupNorm(groups, in_channels, eps=1e-5)
+        self.norm1 = GroupNorm(groups, in_channels, eps=1e-5)
         self.conv1 = nn.Conv2d(in_channels, out_channels, 3, padding=1)
         self.time_emb_proj = nn.Linear(temb_channels, out_channels)
-        self.norm2 = nn.GroupNorm(groups, out_channels, eps=1e-5)
+        self.norm2 = GroupNorm(groups, out_channels, eps=1e-5)
         self.dropout = nn.Dropout(0.0)
         self.conv2 = nn.Conv2d(out_channels, out_channels, 3, padding=1)
         self.nonlinearity = nn.SiLU()
@@ -382,7 +408,7 @@ class UNet2DConditionModel(nn.Module):
             else:
                 up.append(CrossAttnUpBlock2D(cin, cout, prev, temb, L + 1, rev_heads[i], ctx, g, lp, not last))
         self.up_blocks = nn.ModuleList(up)
-        self.conv_norm_out = nn.GroupNorm(g, ch[0], eps=1e-5)
+        self.conv_norm_out = GroupNorm(g, ch[0], eps=1e-5)
         self.conv_act = nn.SiLU()
         self.conv_out = nn.Conv2d(ch[0], cfg.out_channels, 3, padding=1)
 
