@@ -17,6 +17,15 @@ namespace {
 
 constexpr int kWarpsPerBlock = 8;
 
+// x / y with one reciprocal per row: q = x*r, then one Newton correction q + (x - y*q)*r (Markstein).
+// With r the correctly rounded 1/y this is the correctly rounded quotient except in rare half-ulp
+// cases — i.e. the IEEE division the reference's `x / norm` performs, at 3 FMA-pipe instructions per
+// element instead of a MUFU.RCP + fix-up sequence per element (the kernel was XU-bound on divisions).
+__device__ __forceinline__ float div_by(float x, float y, float r) {
+  const float q = x * r;
+  return fmaf(fmaf(-y, q, x), r, q);
+}
+
 template <bool kInF32>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 unit_rows_kernel(const void* __restrict__ x, long long rows, int dim, long long row_stride,
@@ -44,13 +53,14 @@ unit_rows_kernel(const void* __restrict__ x, long long rows, int dim, long long 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     const float nrm = (float)sqrt(ss);
+    const float rcp = __frcp_rn(nrm);
     __half* orow = out + r * dim;
     if (kInF32) {
       const float* xr = static_cast<const float*>(x) + r * row_stride;
       for (int c = lane * 4; c < dim; c += 128) {
         float4 v = *reinterpret_cast<const float4*>(xr + c);
-        __half2 lo = __floats2half2_rn(__fdiv_rn(v.x, nrm), __fdiv_rn(v.y, nrm));
-        __half2 hi = __floats2half2_rn(__fdiv_rn(v.z, nrm), __fdiv_rn(v.w, nrm));
+        __half2 lo = __floats2half2_rn(div_by(v.x, nrm, rcp), div_by(v.y, nrm, rcp));
+        __half2 hi = __floats2half2_rn(div_by(v.z, nrm, rcp), div_by(v.w, nrm, rcp));
         uint2 o2;
         o2.x = *reinterpret_cast<uint32_t*>(&lo);
         o2.y = *reinterpret_cast<uint32_t*>(&hi);
@@ -62,8 +72,8 @@ unit_rows_kernel(const void* __restrict__ x, long long rows, int dim, long long 
         uint2 raw = *reinterpret_cast<const uint2*>(xr + c);
         float2 a = __half22float2(*reinterpret_cast<__half2*>(&raw.x));
         float2 b = __half22float2(*reinterpret_cast<__half2*>(&raw.y));
-        __half2 lo = __floats2half2_rn(__fdiv_rn(a.x, nrm), __fdiv_rn(a.y, nrm));
-        __half2 hi = __floats2half2_rn(__fdiv_rn(b.x, nrm), __fdiv_rn(b.y, nrm));
+        __half2 lo = __floats2half2_rn(div_by(a.x, nrm, rcp), div_by(a.y, nrm, rcp));
+        __half2 hi = __floats2half2_rn(div_by(b.x, nrm, rcp), div_by(b.y, nrm, rcp));
         uint2 o2;
         o2.x = *reinterpret_cast<uint32_t*>(&lo);
         o2.y = *reinterpret_cast<uint32_t*>(&hi);
@@ -174,6 +184,7 @@ layernorm_unit_rows_kernel(const __half* __restrict__ x, long long rows, int dim
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     const float nrm = (float)sqrt(ss);
+    const float rcp = __frcp_rn(nrm);
     __half* orow = out + r * dim;
 #pragma unroll
     for (int j = 0; j < kLnMaxVecPerLane; ++j) {
@@ -183,7 +194,7 @@ layernorm_unit_rows_kernel(const __half* __restrict__ x, long long rows, int dim
         __half2* h = reinterpret_cast<__half2*>(&w);
 #pragma unroll
         for (int e = 0; e < 4; ++e)
-          h[e] = __floats2half2_rn(__fdiv_rn(v[j][2 * e], nrm), __fdiv_rn(v[j][2 * e + 1], nrm));
+          h[e] = __floats2half2_rn(div_by(v[j][2 * e], nrm, rcp), div_by(v[j][2 * e + 1], nrm, rcp));
         *reinterpret_cast<uint4*>(orow + vi * 8) = w;
       }
     }

@@ -17,8 +17,11 @@ piv = torch.randn(K, S, dim, device="cuda")
 A = torch.randn(3, K, S, dim, device="cuda").half()
 resid = torch.randn(3 * B, S, dim, device="cuda").half()
 kf_a, kf_b, w = [2] * B, [1] * B, blend_weights(B)
+norm = torch.nn.LayerNorm(dim).cuda().half()
+hid = torch.randn(B, S, dim, device="cuda").half()
 for _ in range(3):
     ops.ext_attn(q, k, v, heads, d ** -0.5, False)
+    ops.layernorm_unit_rows(hid, norm)
     xu, pu = ops.unit_rows(x), ops.unit_rows(piv)
     idx_a, idx_b = ops.nn_field(xu, pu, kf_a, kf_b)
     ops.propagate(A, idx_a, idx_b, kf_a, kf_b, w, resid)
