@@ -65,3 +65,61 @@ def test_strict_dtype_env(monkeypatch):
     idx = torch.randint(0, 16, (2, 16), device="cuda", dtype=torch.int32)
     out = ops.propagate(A, idx, idx, [1, 1], [0, 0], blend_weights(2), None, out_dtype=torch.float32)
     assert out.dtype == torch.float32
+
+
+def test_sd21_shape_block_cuda_vs_reference_gpu_path():
+    """BASELINE C4 shapes at the hook level: one SD2.1-shape transformer block (dim 320, 5 heads x 64) at
+    2304 tokens, SDEdit flavour (no injection): pivotal pass over 3 keyframes + two frame passes, CUDA ops
+    vs the oracle ops under the same autocast."""
+    import torch.nn as nn
+
+    class _U(nn.Module):
+        def __init__(self, block):
+            super().__init__()
+            site = nn.Module()
+            site.transformer_blocks = nn.ModuleList([block])
+            ups = []
+            for _ in range(4):
+                u = nn.Module()
+                u.attentions = nn.ModuleList([site, site, site])
+                ups.append(u)
+            self.up_blocks = nn.ModuleList(ups)
+
+    class _W(nn.Module):
+        def __init__(self, unet):
+            super().__init__()
+            self.unet = unet
+
+    def run(ops):
+        tfu._install_ops_for_testing(ops)
+        torch.manual_seed(3)
+        block = sd_unet.BasicTransformerBlock(320, 5, 64, 1024).cuda().half().eval()
+        model = _W(_U(block))
+        tfu.register_extended_attention(model)
+        tfu.set_tokenflow(model.unet)
+        K, B, S = 3, 2, 2304
+        outs = []
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            h = torch.randn(3 * K, S, 320, device="cuda").half()
+            ctx = torch.randn(3 * K, 77, 1024, device="cuda").half()
+            tfu.register_pivotal(model, True)
+            outs.append(block(h, encoder_hidden_states=ctx).float())
+            tfu.register_pivotal(model, False)
+            for i in (0, 2):
+                hf = (h[:K][i].unsqueeze(0).repeat(B, 1, 1) + 0.3 * torch.randn(B, S, 320, device="cuda").half())
+                hf = torch.cat([hf, torch.randn(2 * B, S, 320, device="cuda").half()])
+                tfu.register_batch_idx(model, i)
+                outs.append(block(hf, encoder_hidden_states=ctx[:3 * B]).float())
+                outs.append(block._tf_nn_idx[0].long().reshape(-1).clone())
+        return outs
+
+    want = run(OracleOps())
+    got = run(None)
+    assert torch.allclose(got[0], want[0], atol=3e-3, rtol=3e-3)          # pivotal pass
+    for j in (1, 3):                                                       # frame passes: (output, NN indices)
+        g_out, w_out, g_idx, w_idx = got[j], want[j], got[j + 1], want[j + 1]
+        same = (g_idx == w_idx)
+        assert (~same).float().mean().item() < 5e-3                       # fp16 tie classes only
+        rows = same.view(1, -1).expand(3, -1).reshape(-1)                  # [3*B*S] rows whose NN index agrees
+        g2, w2 = g_out.reshape(-1, 320)[rows], w_out.reshape(-1, 320)[rows]
+        assert torch.allclose(g2, w2, atol=3e-3, rtol=3e-3)

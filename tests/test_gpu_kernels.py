@@ -311,3 +311,73 @@ def test_ext_attn_uniform_values_full_size(ops):
         ref = torch.softmax(qq @ kk.transpose(1, 2) * d ** -0.5, dim=-1) @ vv
         ref = ref.permute(1, 0, 2).reshape(len(rows), dim)
         assert (got[smp, rows].float() - ref).abs().max().item() < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# other BASELINE configurations (C3: K = 10 keyframes; C4: SD2.1 shapes; C5: K > 12) and the sharded form
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,S,heads,d", [
+    (10, 256, 2, 40),      # C3: 80 frames / stride 8 -> 10 keyframes, 2560 keys per query here
+    (5, 576, 2, 64),       # C4: SD2.1 head dim 64, 576 tokens (24x24 level of a 768^2 frame)
+    (25, 64, 2, 40),       # C5 stride 8: 25 keyframes (the reference's K > 12 per-frame loop)
+])
+def test_ext_attn_other_configs(ops, n, S, heads, d):
+    torch.manual_seed(n + S)
+    dim = heads * d
+    q, k, v = (torch.randn(3 * n, S, dim, device="cuda").half() for _ in range(3))
+    for inject in (False, True):
+        got = ops.ext_attn(q, k, v, heads, d ** -0.5, inject)
+        want = _attn_ref(q, k, v, heads, d ** -0.5, inject)
+        assert torch.allclose(got.float(), want, atol=1e-3, rtol=1.5e-3)
+
+
+def test_ext_attn_table_matches_whole_pass(ops):
+    """The sharded-pass entry point (per-sample q/k/v slab table) reproduces the whole-pass result
+    rank by rank — the arithmetic behind tests/test_sharded_cpu.py, on the CUDA kernel."""
+    from tokenflow_b200.tokenflow_utils import PivotalShard
+    torch.manual_seed(5)
+    K, S, heads, d = 5, 320, 2, 40
+    dim = heads * d
+    q, k, v = (torch.randn(3 * K, S, dim, device="cuda").half() for _ in range(3))
+    for inject in (False, True):
+        whole = ops.ext_attn(q, k, v, heads, d ** -0.5, inject)
+        for G in (2, 8):
+            m = -(-3 * K // G)
+            pad = G * m - 3 * K
+            padded = [torch.cat([t, t[-1:].expand(pad, S, dim)]) if pad else t for t in (q, k, v)]
+            for r in range(G):
+                sh = PivotalShard(G, r, K)
+                q_local = padded[0][r * m:(r + 1) * m]
+                q_src = padded[0] if inject else q_local
+                out = ops.ext_attn_table(q_src, padded[1], padded[2], sh.attention_table(inject), heads, d ** -0.5)
+                for j, i in enumerate(sh.slots):
+                    if i < 3 * K:
+                        assert torch.equal(out[j], whole[i]), (G, r, j)
+
+
+def test_nn_field_sd21_token_counts(ops):
+    """C4: 768^2 frames -> 9216 tokens at the top level (and 2304 one level down)."""
+    for S, dim in ((9216, 320), (2304, 640)):
+        x, piv = _video_like(2, 2, S, dim, seed=S)
+        _check_nn(ops, x, piv, [1, 1], [0, -1])
+
+
+def test_propagate_many_frames_one_launch(ops):
+    """All 40 frames of C2 in one launch (per-frame table spanning 5 batches) == 5 per-batch launches."""
+    from tokenflow_b200.ops import blend_weights
+    torch.manual_seed(11)
+    N, B, K, S, dim = 40, 8, 5, 256, 320
+    A = torch.randn(3, K, S, dim, device="cuda").half()
+    idx_a = torch.randint(0, S, (N, S), device="cuda", dtype=torch.int32)
+    idx_b = torch.randint(0, S, (N, S), device="cuda", dtype=torch.int32)
+    res = torch.randn(3, N, S, dim, device="cuda").half()
+    w = blend_weights(B)
+    kf_a = [g // B for g in range(N)]
+    kf_b = [g // B - 1 if g >= B else -1 for g in range(N)]
+    ww = [w[g % B] for g in range(N)]
+    one = ops.propagate(A, idx_a, idx_b, kf_a, kf_b, ww, res.view(3 * N, S, dim)).view(3, N, S, dim)
+    for i in range(K):
+        sl = slice(i * B, (i + 1) * B)
+        part = ops.propagate(A, idx_a[sl], idx_b[sl] if i > 0 else None, kf_a[sl], kf_b[sl], ww[sl],
+                             res[:, sl].reshape(3 * B, S, dim)).view(3, B, S, dim)
+        assert torch.equal(one[:, sl], part)
