@@ -110,7 +110,9 @@ def build_editor(device, world=1, rank=0, seed=1, channels_last=True, frames_per
     from tokenflow_b200 import sd_unet, tokenflow_utils as tfu
     from tokenflow_b200.editor import TokenFlowEditor, synthetic_inputs
     from tokenflow_b200.scheduler import DDIMScheduler
-    unet = sd_unet.build_unet("sd15", seed=seed, device=device, dtype=torch.float16)
+    # multi-GPU: draw the weights on the device (torchrun pins OMP_NUM_THREADS=1 and a CPU init of the 860M
+    # parameters then takes minutes per rank); single GPU keeps the device-independent CPU init
+    unet = sd_unet.build_unet("sd15", seed=seed, device=device, dtype=torch.float16, init_on_device=world > 1)
     if channels_last:
         unet = unet.to(memory_format=torch.channels_last)
     cfg = {"n_frames": N_FRAMES, "batch_size": BATCH, "n_timesteps": N_TIMESTEPS, "guidance_scale": 7.5,
@@ -130,6 +132,7 @@ def run_ours(args):
     device = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
+        os.environ["NCCL_DEBUG"] = os.environ.get("TF_BENCH_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=device)
     from tokenflow_b200 import tokenflow_utils as tfu
     ops = tfu._ops()                                     # CudaOps: raises if the .so / B200 is missing

@@ -72,17 +72,3 @@ def load_reference():
         else:
             del sys.modules["util"]
     return ref_tf, ref_util
-
-
-class RefWrapper:
-    """The object the reference calls `model`: something with `.unet` (Appendix B)."""
-
-    def __init__(self, unet):
-        import torch.nn as nn
-
-        class _W(nn.Module):
-            def __init__(self, unet):
-                super().__init__()
-                self.unet = unet
-
-        self.module = _W(unet)

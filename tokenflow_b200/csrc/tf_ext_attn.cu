@@ -324,21 +324,25 @@ ext_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 
 
 // ================================================================================================
-// Ping-pong kernel (head dim <= 64): two 128-query tiles per CTA, 64-key score tiles, every score
-// tile double-buffered in TMEM.
+// Ping-pong kernel (head dim <= 64): two 128-query tiles per CTA.
 //
 // The softmax inner loop is MUFU-bound on this chip (ex2: 8.1 cycles per warp instruction per SM
 // sub-partition, profiles/r01_pipe_throughput_ubench.txt; at d = 40 the two MMAs of a 128x128 tile
-// need only ~450 tensor cycles against ~1040 MUFU cycles), so the design goal is to keep two softmax
-// warps per sub-partition permanently busy:
-//   * two query tiles A and B (warps 2-5 / 6-9) share every K/V tile (fetched once per 256 queries);
-//   * S_X[t+2] = Q_X K_{t+2}^T is issued right after P_X[t] V_t, into the buffer P_X[t] just vacated,
-//     so a softmax warp never waits for the tensor pipe in steady state;
-//   * each softmax thread holds its 64-column score row in registers (one TMEM read per tile);
-//   * row sums come from an extra N=16 tcgen05.mma of P against a constant tile of ones, accumulated in
-//     TMEM from exactly the fp16 probabilities that feed P V (numerator and denominator consistent).
+// need only ~450 tensor cycles against ~1040 MUFU cycles), and a tcgen05.mma costs its issuing thread
+// 45-100 cycles whatever its shape (profiles/r01_ext_attn_trace.md).  The structure follows from that:
+//   * two query tiles A and B share every K/V tile (fetched once per 256 queries);
+//   * one MMA-issuer warp per query tile, so the two issue streams run in parallel; operands stay
+//     warp-uniform so ptxas emits back-to-back UTCHMMA;
+//   * each softmax thread holds its whole score row in registers (one TMEM read per tile), takes the
+//     row max with FMNMX3, rescales O lazily, writes fp16 P over the score columns and keeps the row
+//     sum in a register;
+//   * the two softmax warps that share an SM sub-partition (and its MUFU) take turns in their exp2
+//     phase through an mbarrier token, handed over at 3/4 of the loop.
+// kBlockN = 128 (default): one score buffer per query tile, S_X[t+1] issued right after P_X[t] V_t.
+// kBlockN = 64: two score buffers per query tile, S_X[t+2] issued after P_X[t] V_t (more, smaller MMAs:
+// measured slower at d = 40; kept selectable with TF_EXT_ATTN_MODE=pp64).
 //   warp 0: TMA   warps 1,2: MMA issue for tile A / B   warp 3: spare   warps 4-7: softmax A   warps 8-11: softmax B
-// TMEM: S_A[0] S_A[1] S_B[0] S_B[1] = 4 x 64 columns, O_A [256,320) O_B [320,384) L_A [384,400) L_B [400,416)
+// TMEM: score buffers [0,256), O_A [256,320), O_B [320,384)
 // ================================================================================================
 constexpr int kPPStagesMax = 12;
 struct AttnCtl2 {
@@ -354,8 +358,6 @@ struct AttnCtl2 {
   uint32_t tmem_base;
 };
 
-// kBlockN = 128: one score buffer per query tile (S_X[t+1] is issued after P_X[t] V_t);
-// kBlockN =  64: two score buffers per query tile (S_X[t+2] is issued after P_X[t] V_t).
 template <int kBlockN>
 __global__ void __launch_bounds__(384, 1)
 ext_attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,

@@ -430,10 +430,26 @@ class UNet2DConditionModel(nn.Module):
         return UNetOutput(sample=x)
 
 
-def build_unet(kind: str = "sd15", seed: int = 1, device="cpu", dtype=torch.float32) -> UNet2DConditionModel:
+def build_unet(kind: str = "sd15", seed: int = 1, device="cpu", dtype=torch.float32,
+               init_on_device: bool = False) -> UNet2DConditionModel:
     """Random-init (default PyTorch inits) SD-shape UNet, seeded like the reference default
-    (configs/config_pnp.yaml:2)."""
+    (configs/config_pnp.yaml:2).  By default the parameters are drawn on the CPU (device independent, what
+    the tests and golden vectors use) and moved; `init_on_device=True` draws them directly on `device`
+    (much faster under torchrun's OMP_NUM_THREADS=1; identical on every rank for a given seed and device
+    type, but a different random stream than the CPU init)."""
     cfg = {"sd15": sd15_config, "sd21": sd21_config, "tiny": tiny_config}[kind]()
+    if init_on_device and torch.device(device).type == "cuda":
+        try:
+            cuda_state = torch.cuda.get_rng_state(device)
+            torch.cuda.manual_seed(seed)
+            try:
+                with torch.device(device):
+                    net = UNet2DConditionModel(cfg)
+            finally:
+                torch.cuda.set_rng_state(cuda_state, device)
+            return net.to(dtype=dtype).eval()
+        except Exception:  # noqa: BLE001  — fall back to the CPU init below
+            pass
     gen_state = torch.random.get_rng_state()
     torch.manual_seed(seed)
     try:
