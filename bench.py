@@ -32,6 +32,7 @@ if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
 N_FRAMES, BATCH, N_TIMESTEPS, LATENT = 40, 8, 50, 64
+METRIC = "frames/sec for 40-frame 512x512 SD1.5 50-step edit"
 WORKLOAD = "C2: 40-frame 512x512 SD1.5 PnP 50-step edit, B=8 (K=5 keyframes), random-init UNet fp16, synthetic latents"
 
 
@@ -245,7 +246,7 @@ def run_ours(args):
     cpu = cpu_baseline_sample() if (world == 1 and not args.no_cpu_baseline) else None
 
     line = {
-        "metric": "frames/sec", "value": round(fps, 4), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "metric": METRIC, "value": round(fps, 4), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "n_frames": N_FRAMES, "keyframes": N_FRAMES // BATCH, "ddim_steps": N_TIMESTEPS,
@@ -373,7 +374,7 @@ def run_reference(args):
     t_step = sum(times) / len(times)
     fps = N_FRAMES / (N_TIMESTEPS * t_step)
     cores = torch.get_num_threads()
-    line = {"impl": "reference", "metric": "frames/sec", "value": round(fps, 6), "unit": "frames/s", "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": METRIC, "value": round(fps, 6), "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t_step * 1e3, 1), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "note": "reference algorithm (oracle port) on host cores; each step is a bounded "

@@ -192,7 +192,7 @@ def test_frames_per_pass_equals_reference_schedule(golden_dir):
     """All frames in one frame pass (per-frame keyframe table) == the reference's per-batch passes."""
     tfu._install_ops_for_testing(OracleOps())
     c = _load(golden_dir, "unet_c1_pnp.pt")
-    cfg = dict(c["config"], frames_per_pass=cfg_frames if (cfg_frames := c["config"]["n_frames"]) else 4)
+    cfg = dict(c["config"], frames_per_pass=c["config"]["n_frames"])
     unet = sd_unet.build_unet("tiny", seed=c["seed"])
     x, text, pnp, src = synthetic_inputs(cfg["n_frames"], c["latent"], unet.config.cross_attention_dim,
                                          cfg["n_timesteps"], seed=c["seed"], ctx_len=c["ctx_len"])
