@@ -107,7 +107,7 @@ def dist_env():
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def build_editor(device, world=1, rank=0, seed=1, channels_last=True, frames_per_pass=BATCH):
+def build_editor(device, world=1, rank=0, seed=1, channels_last=True, frames_per_pass=BATCH, fused_pass=True):
     from tokenflow_b200 import sd_unet, tokenflow_utils as tfu
     from tokenflow_b200.editor import TokenFlowEditor, synthetic_inputs
     from tokenflow_b200.scheduler import DDIMScheduler
@@ -117,7 +117,8 @@ def build_editor(device, world=1, rank=0, seed=1, channels_last=True, frames_per
     if channels_last:
         unet = unet.to(memory_format=torch.channels_last)
     cfg = {"n_frames": N_FRAMES, "batch_size": BATCH, "n_timesteps": N_TIMESTEPS, "guidance_scale": 7.5,
-           "mode": "pnp", "pnp_attn_t": 0.5, "pnp_f_t": 0.8, "frames_per_pass": frames_per_pass}
+           "mode": "pnp", "pnp_attn_t": 0.5, "pnp_f_t": 0.8, "frames_per_pass": frames_per_pass,
+           "fused_pass": bool(fused_pass)}
     x, text, pnp, src = synthetic_inputs(N_FRAMES, LATENT, unet.config.cross_attention_dim, N_TIMESTEPS, seed=seed,
                                          device=device, dtype=torch.float16)
     ed = TokenFlowEditor(unet, DDIMScheduler(), tfu, cfg, text, pnp, source_latents=lambda t: src[t],
@@ -139,7 +140,7 @@ def run_ours(args):
     ops = tfu._ops()                                     # CudaOps: raises if the .so / B200 is missing
     torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)
     ed, x0, src = build_editor(device, world, rank, channels_last=not args.no_channels_last,
-                               frames_per_pass=args.frames_per_pass)
+                               frames_per_pass=args.frames_per_pass, fused_pass=bool(args.fused_pass))
     timesteps = [int(t) for t in ed.scheduler.timesteps]
     indices = torch.arange(N_FRAMES)
 
@@ -252,7 +253,8 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "n_frames": N_FRAMES, "keyframes": N_FRAMES // BATCH, "ddim_steps": N_TIMESTEPS,
                    "frames_per_sec_definition": "n_frames / (50 * mean denoising-step time over the timed steps)",
                    "parallelism": f"frames sharded over {world} GPU(s)" if world > 1 else "single GPU",
-                   "frames_per_pass": (N_FRAMES // world) if world > 1 else args.frames_per_pass,
+                   "frames_per_pass": (N_FRAMES // world) if (world > 1 or args.fused_pass) else args.frames_per_pass,
+                   "unet_calls_per_step": 1 if args.fused_pass else (2 if world > 1 else 1 + -(-N_FRAMES // args.frames_per_pass)),
                    "l2": "inputs > L2: every step streams ~10 GB of activations through the UNet (no flush needed)"},
         "e2e": {"value": round(fps_e2e, 4), "unit": "frames/s", "ms_per_step": round(ms_step_e2e, 3),
                 "h2d_bytes_per_step": 2 * lat_bytes, "d2h_bytes_per_step": lat_bytes},
@@ -397,6 +399,9 @@ def main():
     ap.add_argument("--frames-per-pass", type=int, default=N_FRAMES,
                     help="frames per frame-pass UNet call (8 = the reference's per-batch schedule; default: all "
                          "frames of the GPU in one pass with per-frame keyframe tables — identical results)")
+    ap.add_argument("--fused-pass", type=int, default=1,
+                    help="1: one UNet call per step and GPU ([pivotal samples | frames], keyframe caches filled and "
+                         "consumed inside each block); 0: the reference's pivotal pass + frame passes")
     ap.add_argument("--cudnn-benchmark", type=int, default=1, help="torch.backends.cudnn.benchmark for the UNet body convs")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -19,11 +19,11 @@ from tokenflow_b200.scheduler import DDIMScheduler
 pytestmark = pytest.mark.gpu
 
 
-def _run(ops, mode, n_frames=4, batch=2, steps=2, latent=16, seed=1, kind="tiny"):
+def _run(ops, mode, n_frames=4, batch=2, steps=2, latent=16, seed=1, kind="tiny", fused=False):
     tfu._install_ops_for_testing(ops)
     unet = sd_unet.build_unet(kind, seed=seed, device="cuda", dtype=torch.float16)
     cfg = {"n_frames": n_frames, "batch_size": batch, "n_timesteps": steps, "guidance_scale": 7.5,
-           "mode": mode, "pnp_attn_t": 0.5, "pnp_f_t": 0.8, "start": 0.9}
+           "mode": mode, "pnp_attn_t": 0.5, "pnp_f_t": 0.8, "start": 0.9, "fused_pass": fused}
     x, text, pnp, src = synthetic_inputs(n_frames, latent, unet.config.cross_attention_dim, steps, seed=seed,
                                          device="cuda", dtype=torch.float16, ctx_len=7)
     ed = TokenFlowEditor(unet, DDIMScheduler(), tfu, cfg, text, pnp, source_latents=lambda t: src[t])
@@ -123,3 +123,13 @@ def test_sd21_shape_block_cuda_vs_reference_gpu_path():
         rows = same.view(1, -1).expand(3, -1).reshape(-1)                  # [3*B*S] rows whose NN index agrees
         g2, w2 = g_out.reshape(-1, 320)[rows], w_out.reshape(-1, 320)[rows]
         assert torch.allclose(g2, w2, atol=3e-3, rtol=3e-3)
+
+
+@pytest.mark.parametrize("mode,steps", [("pnp", 2), ("sdedit", 10)])
+def test_fused_pass_cuda(mode, steps):
+    """One UNet call per step ([pivotal samples | frames]) on the CUDA kernels == separate passes."""
+    want, kf_w, _ = _run(None, mode, steps=steps)
+    got, kf_g, _ = _run(None, mode, steps=steps, fused=True)
+    assert kf_g == kf_w and torch.isfinite(got).all()
+    rel = (got - want).norm() / want.norm()
+    assert rel.item() < 2e-2, rel.item()

@@ -202,3 +202,25 @@ def test_frames_per_pass_equals_reference_schedule(golden_dir):
     out = ed.sample_loop(x)
     assert ed.keyframe_log == c["keyframes"]
     assert torch.allclose(out, c["out"], atol=2e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("name", ["unet_c1_pnp.pt", "unet_c1_sdedit.pt"])
+def test_fused_pass_equals_reference_schedule(golden_dir, name):
+    """ONE UNet call per step ([pivotal samples | all frames]) == the reference's pivotal pass + N/B frame
+    passes, including the PnP conv-feature injection on both parts of the batch."""
+    tfu._install_ops_for_testing(OracleOps())
+    c = _load(golden_dir, name)
+    cfg = dict(c["config"], fused_pass=True)
+    unet = sd_unet.build_unet("tiny", seed=c["seed"])
+    x, text, pnp, src = synthetic_inputs(cfg["n_frames"], c["latent"], unet.config.cross_attention_dim,
+                                         cfg["n_timesteps"], seed=c["seed"], ctx_len=c["ctx_len"])
+    ed = TokenFlowEditor(unet, DDIMScheduler(), tfu, cfg, text, pnp, source_latents=lambda t: src[t])
+    ed.init_method()
+    torch.manual_seed(c["seed"])
+    steps = []
+    out = ed.sample_loop(x, on_step=lambda i, t, z: steps.append(z.clone()))
+    assert ed.keyframe_log == c["keyframes"]
+    for got, want in zip(steps, c["steps"]):
+        assert torch.allclose(got, want, atol=2e-4, rtol=1e-4)
+    assert torch.allclose(out, c["out"], atol=2e-4, rtol=1e-4)
+    assert all(getattr(b, "_tf_fused", 0) == 0 for b in tfu._transformer_blocks(ed))   # mode restored

@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-def _edit(world, rank, mode, steps):
+def _edit(world, rank, mode, steps, fused=False):
     from oracle.oracle_ops import OracleOps
     from tokenflow_b200 import sd_unet
     from tokenflow_b200.editor import TokenFlowEditor, synthetic_inputs
@@ -28,7 +28,7 @@ def _edit(world, rank, mode, steps):
     tfu._install_ops_for_testing(OracleOps())
     unet = sd_unet.build_unet("tiny", seed=1)
     cfg = {"n_frames": 8, "batch_size": 2, "n_timesteps": steps, "guidance_scale": 7.5, "mode": mode,
-           "pnp_attn_t": 0.5, "pnp_f_t": 0.8, "start": 0.9}
+           "pnp_attn_t": 0.5, "pnp_f_t": 0.8, "start": 0.9, "fused_pass": fused}
     x, text, pnp, src = synthetic_inputs(8, 16, unet.config.cross_attention_dim, steps, seed=1, ctx_len=7)
     ed = TokenFlowEditor(unet, DDIMScheduler(), tfu, cfg, text, pnp, source_latents=lambda t: src[t],
                          world_size=world, rank=rank)
@@ -37,25 +37,26 @@ def _edit(world, rank, mode, steps):
     return ed.sample_loop(x), ed.keyframe_log
 
 
-def _worker(rank, world, port, mode, steps, q):
+def _worker(rank, world, port, mode, steps, q, fused=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.set_num_threads(2)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        out, kf = _edit(world, rank, mode, steps)
+        out, kf = _edit(world, rank, mode, steps, fused)
         q.put((rank, out, kf))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode,steps", [("pnp", 2), ("sdedit", 10)])
-def test_two_rank_edit_equals_single_process(mode, steps):
+@pytest.mark.parametrize("mode,steps,fused", [("pnp", 2, False), ("sdedit", 10, False), ("pnp", 2, True),
+                                              ("sdedit", 10, True)])
+def test_two_rank_edit_equals_single_process(mode, steps, fused):
     want, kf_want = _edit(1, 0, mode, steps)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, steps, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, steps, q, fused)) for r in range(2)]
     for p in procs:
         p.start()
     results = [q.get(timeout=300) for _ in procs]

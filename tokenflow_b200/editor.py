@@ -97,7 +97,13 @@ class TokenFlowEditor(nn.Module):
         return torch.randint(batch_size, (n // batch_size,)) + torch.arange(0, n, batch_size)
 
     def batched_denoise_step(self, x, t, indices):
-        """run_tokenflow_pnp.py:220-233 (one process), or its frame-sharded form (world_size > 1)."""
+        """run_tokenflow_pnp.py:220-233 (one process), or its frame-sharded form (world_size > 1).
+        With config["fused_pass"] the pivotal samples and the frame samples go through the UNet in ONE
+        call (the keyframe caches a block fills from the first part of the batch are consumed by the
+        second part inside the same block) — identical arithmetic, half the kernel launches."""
+        if self.config.get("fused_pass", False):
+            with self._autocast():
+                return self._fused_step(x, t, indices)
         if self.world_size > 1:
             with self._autocast():
                 return self._sharded_step(x, t, indices)
@@ -174,6 +180,59 @@ class TokenFlowEditor(nn.Module):
         _, npu, npc = noise_pred.chunk(3)
         noise_pred = npu + self.config["guidance_scale"] * (npc - npu)
         x_local = self.scheduler.step(noise_pred, t, xs)['prev_sample'].contiguous()
+        out = torch.empty_like(x)
+        dist.all_gather_into_tensor(out, x_local, group=self.group)
+        return out
+
+    @torch.no_grad()
+    def _fused_step(self, x, t, indices):
+        """One UNet call per denoising step and rank: [pivotal samples | this rank's frames x 3 streams]."""
+        h, G, r = self.hooks, self.world_size, self.rank
+        N, B = len(x), self.config["batch_size"]
+        K = N // B
+        assert N % G == 0, "frames must divide evenly over the ranks"
+        pivotal_idx = self.draw_keyframes(N)
+        self.keyframe_log.append(pivotal_idx.tolist())
+        src_all = self.source_latents_t(int(t))[indices].to(x.device, x.dtype)
+        h.register_time(self, int(t))
+        if G == 1:                                            # the reference's pivotal batch: [src | uncond | cond] x K
+            shard = None
+            piv_lat = torch.cat([src_all[pivotal_idx], x[pivotal_idx], x[pivotal_idx]])
+            piv_emb = torch.cat([self.pnp_guidance_embeds.repeat(K, 1, 1),
+                                 torch.repeat_interleave(self.text_embeds, K, dim=0)])
+        else:                                                 # this rank's m of the 3K (stream, keyframe) samples
+            shard = h.PivotalShard(G, r, K, self.group)
+            lat, emb = [], []
+            for i in shard.slots:
+                i = min(i, 3 * K - 1)                         # padding slots recompute the last sample
+                s_, f_ = divmod(i, K)
+                frame = int(pivotal_idx[f_])
+                lat.append(src_all[frame] if s_ == 0 else x[frame])
+                emb.append(self.pnp_guidance_embeds[0] if s_ == 0 else self.text_embeds[s_ - 1])
+            piv_lat, piv_emb = torch.stack(lat), torch.stack(emb)
+        per = N // G
+        lo = r * per
+        frames = list(range(lo, lo + per))
+        xs, srcs = x[lo:lo + per], src_all[lo:lo + per]
+        n_piv = piv_lat.shape[0]
+        latent_model_input = torch.cat([piv_lat, srcs, xs, xs])
+        text = torch.cat([piv_emb, self.pnp_guidance_embeds.repeat(per, 1, 1),
+                          torch.repeat_interleave(self.text_embeds, per, dim=0)])
+        h.register_pivotal(self, False)
+        h.register_shard(self, shard)
+        h.register_frame_table(self, *self.frame_table(frames))
+        h.register_fused(self, n_piv)
+        try:
+            noise_pred = self.unet(latent_model_input, t, encoder_hidden_states=text)['sample'][n_piv:]
+        finally:
+            h.register_fused(self, 0)
+            h.register_shard(self, None)
+        _, npu, npc = noise_pred.chunk(3)
+        noise_pred = npu + self.config["guidance_scale"] * (npc - npu)
+        x_local = self.scheduler.step(noise_pred, t, xs)['prev_sample'].contiguous()
+        if G == 1:
+            return x_local
+        import torch.distributed as dist
         out = torch.empty_like(x)
         dist.all_gather_into_tensor(out, x_local, group=self.group)
         return out

@@ -32,7 +32,8 @@ import torch
 from .util import isinstance_str, batch_cosine_sim  # noqa: F401  (re-exported like the reference)
 
 __all__ = [
-    "register_pivotal", "register_batch_idx", "register_frame_table", "register_shard", "PivotalShard",
+    "register_pivotal", "register_batch_idx", "register_frame_table", "register_shard", "register_fused",
+    "PivotalShard",
     "register_time", "load_source_latents_t",
     "register_conv_injection", "register_extended_attention_pnp", "register_extended_attention",
     "make_tokenflow_attention_block", "set_tokenflow", "isinstance_str", "batch_cosine_sim",
@@ -143,6 +144,16 @@ class PivotalShard:
         return tab
 
 
+def register_fused(diffusion_model, n_pivotal: int):
+    """Fused pass: the next UNet call carries `n_pivotal` pivotal samples followed by the frame samples
+    ([source | uncond | cond] thirds).  0 restores the reference's separate passes."""
+    for module in _transformer_blocks(diffusion_model):
+        module._tf_fused = int(n_pivotal)
+    unet = getattr(diffusion_model, "unet", None)
+    if unet is not None:
+        unet.up_blocks[1].resnets[1]._tf_fused = int(n_pivotal)
+
+
 def register_shard(diffusion_model, shard: Optional[PivotalShard]):
     """Install (or clear, with None) the multi-GPU pivotal-pass context on every TokenFlow block."""
     for module in _transformer_blocks(diffusion_model):
@@ -243,15 +254,27 @@ def register_conv_injection(model, injection_schedule):
                 h = h * (1 + scale) + shift
             h = res.conv2(res.dropout(res.nonlinearity(h)))
             if _in_schedule(res):
+                def inject_thirds(part):
+                    n = part.shape[0] // 3
+                    part[n:2 * n] = part[:n]    # uncond <- source   (:89)
+                    part[2 * n:] = part[:n]     # cond   <- source   (:91)
+
+                def inject_sharded(part, shard):   # sharded pivotal samples: the source sample may be remote
+                    part_all = shard.all_gather(part)
+                    return part_all[[i % shard.K if i < 3 * shard.K else i for i in shard.slots]]
+
                 shard = getattr(res, "_tf_shard", None)
-                if shard is None:
-                    n = h.shape[0] // 3
-                    h[n:2 * n] = h[:n]          # uncond <- source   (:89)
-                    h[2 * n:] = h[:n]           # cond   <- source   (:91)
-                else:                           # sharded pivotal pass: the source sample may be remote
-                    h_all = shard.all_gather(h)
-                    src = [i % shard.K if i < 3 * shard.K else i for i in shard.slots]
-                    h = h_all[src]
+                n_piv = getattr(res, "_tf_fused", 0)
+                if n_piv:                       # fused pass: [pivotal samples | frame samples]
+                    if shard is None:
+                        inject_thirds(h[:n_piv])
+                    else:
+                        h[:n_piv] = inject_sharded(h[:n_piv], shard)
+                    inject_thirds(h[n_piv:])
+                elif shard is None:
+                    inject_thirds(h)
+                else:
+                    h = inject_sharded(h, shard)
             if res.conv_shortcut is not None:
                 skip = res.conv_shortcut(skip)
             return (skip + h) / res.output_scale_factor
@@ -342,23 +365,43 @@ def make_tokenflow_attention_block(block_class: Type[torch.nn.Module]) -> Type[t
                 raise NotImplementedError(
                     "tokenflow_b200: AdaLayerNorm transformer blocks are not part of any Stable-Diffusion "
                     "UNet and are not supported by the B200 hot path")
-            batch_size, sequence_length, dim = hidden_states.shape
-            n_frames = batch_size // 3
-            ops = _ops()
             cross_attention_kwargs = cross_attention_kwargs if cross_attention_kwargs is not None else {}
-            if self.pivotal_pass:
-                norm_hidden_states = self.norm1(hidden_states)
+            n_piv = getattr(self, "_tf_fused", 0)
+            if n_piv:
+                # fused pass: the batch is [pivotal samples | frame samples]; the keyframe caches filled by the
+                # first part are consumed by the second within the same block call, so one UNet pass does the
+                # work of the reference's pivotal pass + frame passes (identical arithmetic, half the launches)
+                piv = self._tf_pivotal(hidden_states[:n_piv],
+                                       None if encoder_hidden_states is None else encoder_hidden_states[:n_piv],
+                                       cross_attention_kwargs)
+                frm = self._tf_frames(hidden_states[n_piv:])
+                hidden_states = torch.cat([piv, frm.to(piv.dtype) if frm.dtype != piv.dtype else frm])
+            elif self.pivotal_pass:
+                hidden_states = self._tf_pivotal(hidden_states, encoder_hidden_states, cross_attention_kwargs)
+            else:
+                hidden_states = self._tf_frames(hidden_states)
 
+            if self.attn2 is not None:
+                attn_output = self.attn2(self.norm2(hidden_states), encoder_hidden_states=encoder_hidden_states,
+                                         attention_mask=encoder_attention_mask, **cross_attention_kwargs)
+                hidden_states = attn_output + hidden_states
+            return self.ff(self.norm3(hidden_states)) + hidden_states
+
+        def _tf_pivotal(self, hidden_states, encoder_hidden_states, cross_attention_kwargs):
+            """Self-attention stage of the pivotal pass (reference :311-327, :352-360, :394-397)."""
+            ops = _ops()
+            batch_size, sequence_length, dim = hidden_states.shape
+            norm_hidden_states = self.norm1(hidden_states)
             shard = getattr(self, "_tf_shard", None)
-            if self.pivotal_pass and shard is not None:
+            if shard is not None:
                 # sharded pivotal pass: this rank holds m of the 3K (stream, keyframe) samples
                 unit_all = shard.all_gather(ops.unit_rows(norm_hidden_states))
                 self._tf_pivot_unit = unit_all[:shard.K]                                  # source stream
                 self.pivot_hidden_states = norm_hidden_states
                 self.attn_output = self.attn1(norm_hidden_states, **cross_attention_kwargs)
                 self.kf_attn_output = shard.all_gather(self.attn_output)[:3 * shard.K]
-                hidden_states = self.attn_output + hidden_states
-            elif self.pivotal_pass:
+            else:
+                n_frames = batch_size // 3
                 # cache keyframe features (:326-327) — plus their fp16 unit rows for the NN field
                 self.pivot_hidden_states = norm_hidden_states.view(3, n_frames, sequence_length, dim)
                 self._tf_pivot_unit = ops.unit_rows(self.pivot_hidden_states[0])
@@ -367,29 +410,28 @@ def make_tokenflow_attention_block(block_class: Type[torch.nn.Module]) -> Type[t
                     encoder_hidden_states=encoder_hidden_states if self.only_cross_attention else None,
                     **cross_attention_kwargs)
                 self.kf_attn_output = self.attn_output                                   # :360
-                hidden_states = self.attn_output + hidden_states                          # :397
-            else:
-                table = getattr(self, "_tf_frame_table", None)
-                if table is None:
-                    table = _default_frame_table(self.batch_idx, n_frames)
-                kf_a, kf_b, w = table
-                if len(kf_a) != n_frames:
-                    raise ValueError(f"frame table has {len(kf_a)} entries but the pass has {n_frames} frames")
-                kf = self.kf_attn_output
-                n_kf = kf.shape[0] // 3
-                # norm1 of the source stream only — the other two thirds are never used in this branch (:335)
-                x_unit = ops.layernorm_unit_rows(hidden_states[:n_frames], self.norm1)
-                idx_a, idx_b = ops.nn_field(x_unit, self._tf_pivot_unit, kf_a, kf_b)      # :335-343
-                out_dtype = torch.float32 if (_strict_dtype() and idx_b is not None) else None
-                hidden_states = ops.propagate(kf.view(3, n_kf, sequence_length, dim), idx_a, idx_b, kf_a, kf_b, w,
-                                              residual=hidden_states, out_dtype=out_dtype)   # :361-397
-                self._tf_nn_idx = (idx_a, idx_b)
+            return self.attn_output + hidden_states                                      # :397
 
-            if self.attn2 is not None:
-                attn_output = self.attn2(self.norm2(hidden_states), encoder_hidden_states=encoder_hidden_states,
-                                         attention_mask=encoder_attention_mask, **cross_attention_kwargs)
-                hidden_states = attn_output + hidden_states
-            return self.ff(self.norm3(hidden_states)) + hidden_states
+        def _tf_frames(self, hidden_states):
+            """Self-attention stage of a frame pass: NN field + propagation (reference :329-348, :361-397)."""
+            ops = _ops()
+            batch_size, sequence_length, dim = hidden_states.shape
+            n_frames = batch_size // 3
+            table = getattr(self, "_tf_frame_table", None)
+            if table is None:
+                table = _default_frame_table(self.batch_idx, n_frames)
+            kf_a, kf_b, w = table
+            if len(kf_a) != n_frames:
+                raise ValueError(f"frame table has {len(kf_a)} entries but the pass has {n_frames} frames")
+            kf = self.kf_attn_output
+            n_kf = kf.shape[0] // 3
+            # norm1 of the source stream only — the other two thirds are never used in this branch (:335)
+            x_unit = ops.layernorm_unit_rows(hidden_states[:n_frames], self.norm1)
+            idx_a, idx_b = ops.nn_field(x_unit, self._tf_pivot_unit, kf_a, kf_b)          # :335-343
+            out_dtype = torch.float32 if (_strict_dtype() and idx_b is not None) else None
+            self._tf_nn_idx = (idx_a, idx_b)
+            return ops.propagate(kf.view(3, n_kf, sequence_length, dim), idx_a, idx_b, kf_a, kf_b, w,
+                                 residual=hidden_states, out_dtype=out_dtype)             # :361-397
 
     return TokenFlowBlock
 
