@@ -150,7 +150,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def step_device(x, i):
-        return ed.batched_denoise_step(x, ed.scheduler.timesteps[i % N_TIMESTEPS], indices)
+        return ed.step_index(x, i, indices)          # by schedule index: no device read-back of the timestep
 
     # ---- device-resident measurement (`value`) ----
     torch.manual_seed(1)

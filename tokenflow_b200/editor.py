@@ -48,6 +48,10 @@ class TokenFlowEditor(nn.Module):
         self.keyframe_log = []
         self.world_size, self.rank, self.group = world_size, rank, group
         self._src_override = None
+        # host ints and device scalars of the timesteps, resolved once: the per-step code never has to read
+        # a device tensor back (`int(t)` on a CUDA tensor is a full stream synchronisation)
+        self._t_host = [int(t) for t in self.scheduler.timesteps]
+        self._t_dev = {t: torch.tensor(t, device=self.device) for t in self._t_host}
 
     # ------------------------------------------------------------------------------------
     def init_method(self):
@@ -184,6 +188,22 @@ class TokenFlowEditor(nn.Module):
         dist.all_gather_into_tensor(out, x_local, group=self.group)
         return out
 
+    def _timestep_pair(self, t):
+        """(host int, device scalar) of a timestep without reading the device when `t` is a host value."""
+        t_int = t if isinstance(t, int) else int(t)
+        t_dev = self._t_dev.get(t_int)
+        if t_dev is None:
+            t_dev = self._t_dev[t_int] = torch.tensor(t_int, device=self.device)
+        return t_int, t_dev
+
+    def step_index(self, x, i: int, indices=None):
+        """Denoising step number `i` of the schedule, addressed by index so that no device value is read
+        back on the host (the reference's loop passes a CUDA 0-dim timestep, which costs a stream
+        synchronisation per use)."""
+        if indices is None:
+            indices = torch.arange(len(x))
+        return self.batched_denoise_step(x, self._t_host[i % len(self._t_host)], indices)
+
     @torch.no_grad()
     def _fused_step(self, x, t, indices):
         """One UNet call per denoising step and rank: [pivotal samples | this rank's frames x 3 streams]."""
@@ -191,13 +211,20 @@ class TokenFlowEditor(nn.Module):
         N, B = len(x), self.config["batch_size"]
         K = N // B
         assert N % G == 0, "frames must divide evenly over the ranks"
+        t_int, t = self._timestep_pair(t)
         pivotal_idx = self.draw_keyframes(N)
-        self.keyframe_log.append(pivotal_idx.tolist())
-        src_all = self.source_latents_t(int(t))[indices].to(x.device, x.dtype)
-        h.register_time(self, int(t))
+        kf_list = pivotal_idx.tolist()
+        self.keyframe_log.append(kf_list)
+        src_all = self.source_latents_t(t_int)
+        if not (indices.device.type == "cpu" and indices.numel() == src_all.shape[0]
+                and torch.equal(indices, torch.arange(indices.numel()))):
+            src_all = src_all[indices]                        # (identity in the drivers: all frames, in order)
+        src_all = src_all.to(x.device, x.dtype)
+        h.register_time(self, t_int)
         if G == 1:                                            # the reference's pivotal batch: [src | uncond | cond] x K
             shard = None
-            piv_lat = torch.cat([src_all[pivotal_idx], x[pivotal_idx], x[pivotal_idx]])
+            x_kf = torch.stack([x[j] for j in kf_list])       # host-side index list: no index tensor upload
+            piv_lat = torch.cat([torch.stack([src_all[j] for j in kf_list]), x_kf, x_kf])
             piv_emb = torch.cat([self.pnp_guidance_embeds.repeat(K, 1, 1),
                                  torch.repeat_interleave(self.text_embeds, K, dim=0)])
         else:                                                 # this rank's m of the 3K (stream, keyframe) samples
@@ -229,7 +256,7 @@ class TokenFlowEditor(nn.Module):
             h.register_shard(self, None)
         _, npu, npc = noise_pred.chunk(3)
         noise_pred = npu + self.config["guidance_scale"] * (npc - npu)
-        x_local = self.scheduler.step(noise_pred, t, xs)['prev_sample'].contiguous()
+        x_local = self.scheduler.step(noise_pred, t_int, xs)['prev_sample'].contiguous()
         if G == 1:
             return x_local
         import torch.distributed as dist
@@ -246,7 +273,7 @@ class TokenFlowEditor(nn.Module):
         x = x_host.to(self.device, non_blocking=True)
         self._src_override = (int(t), src_host_t.to(self.device, non_blocking=True))
         try:
-            y = self.batched_denoise_step(x, torch.tensor(int(t), device=self.device), torch.arange(len(x_host)))
+            y = self.batched_denoise_step(x, int(t), torch.arange(len(x_host)))
         finally:
             self._src_override = None
         out_host.copy_(y, non_blocking=True)

@@ -32,14 +32,16 @@ class DDIMScheduler:
         return self.alphas_cumprod[t] if t >= 0 else self.final_alpha_cumprod
 
     def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor):
+        """eta = 0 DDIM update.  The alphas enter as host scalars (the table lives on the CPU), so the
+        update enqueues device work only — no host<->device copy and no stream synchronisation."""
         t = int(timestep)
         prev_t = t - self.num_train_timesteps // self.num_inference_steps
-        a_t = self._alpha(t).to(sample.device)
-        a_prev = self._alpha(prev_t).to(sample.device)
+        a_t = float(self._alpha(t))
+        a_prev = float(self._alpha(prev_t))
         pred_x0 = (sample - (1 - a_t) ** 0.5 * model_output) / a_t ** 0.5
         prev = a_prev ** 0.5 * pred_x0 + (1 - a_prev) ** 0.5 * model_output
         return {"prev_sample": prev}
 
     def add_noise(self, original: torch.Tensor, noise: torch.Tensor, timestep):
-        a = self.alphas_cumprod[int(timestep)].to(original.device)
+        a = float(self.alphas_cumprod[int(timestep)])
         return (a ** 0.5 * original + (1 - a) ** 0.5 * noise).to(original.dtype)
