@@ -285,10 +285,10 @@ class TokenFlowEditor(nn.Module):
         """run_tokenflow_pnp.py:264-273 without the VAE decode."""
         if indices is None:
             indices = torch.arange(len(x))
-        for i, t in enumerate(self.scheduler.timesteps):
+        for i, t in enumerate(self._t_host):          # host ints: nothing is read back from the device per step
             x = self.batched_denoise_step(x, t, indices)
             if on_step is not None:
-                on_step(i, int(t), x)
+                on_step(i, t, x)
         return x
 
 
