@@ -293,7 +293,9 @@ class CpuSampler:
                keys of an extended stream, at each of the 4 UNet levels; x heads x (2K+1) x blocks
                (uncond+cond: K query frames x K*S keys each; source: K frames x S keys = 1 such unit)"""
 
-    def __init__(self):
+    SD15_LEVELS = ((4096, 320, 8, 5), (1024, 640, 8, 5), (256, 1280, 8, 5), (64, 1280, 8, 1))   # (S, dim, heads, blocks)
+
+    def __init__(self, kind="sd15", latent=LATENT, ctx_dim=768, levels=None):
         from oracle.oracle_ops import OracleOps
         from tokenflow_b200 import sd_unet, tokenflow_utils as tfu
         from tokenflow_b200.editor import TokenFlowEditor, synthetic_inputs
@@ -316,9 +318,10 @@ class CpuSampler:
         self.ops = TimedOracle()
         tfu._install_ops_for_testing(self.ops)
         with torch.no_grad():
-            unet = sd_unet.build_unet("sd15", seed=1)
+            self.levels = levels or self.SD15_LEVELS
+            unet = sd_unet.build_unet(kind, seed=1)
             cfg = {"n_frames": 1, "batch_size": 1, "n_timesteps": N_TIMESTEPS, "guidance_scale": 7.5, "mode": "pnp"}
-            self.x, text, pnp, src = synthetic_inputs(1, LATENT, 768, N_TIMESTEPS, seed=1)
+            self.x, text, pnp, src = synthetic_inputs(1, latent, ctx_dim, N_TIMESTEPS, seed=1)
             self.ed = TokenFlowEditor(unet, DDIMScheduler(), tfu, cfg, text, pnp, source_latents=lambda t: src[t])
             self.ed.init_method()
             self.t0 = self.ed.scheduler.timesteps[0]
@@ -341,7 +344,7 @@ class CpuSampler:
                 t_nn_pair, t_prop_frame = self.ops.t["nn"], self.ops.t["prop"]
                 t_body_sample = (t_pass - t_nn_pair - t_prop_frame) / 3.0
                 t_attn = 0.0
-                for S, dim, heads, blocks in ((4096, 320, 8, 5), (1024, 640, 8, 5), (256, 1280, 8, 5), (64, 1280, 8, 1)):
+                for S, dim, heads, blocks in self.levels:
                     d = dim // heads
                     q = torch.randn(1, S, d)
                     k, v = torch.randn(1, K * S, d), torch.randn(1, K * S, d)
