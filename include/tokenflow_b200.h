@@ -28,8 +28,8 @@ extern "C" {
 
 typedef void* tf_stream_t; /* cudaStream_t */
 
-#define TF_MAX_FRAMES 64        /* frames per tf_nn_field / tf_propagate call        */
-#define TF_MAX_ATTN_SAMPLES 160 /* output samples (stream, keyframe) per attention call */
+#define TF_MAX_FRAMES 64        /* frames per kernel launch; tf_nn_field / tf_propagate take any F and chunk */
+#define TF_MAX_ATTN_SAMPLES 160 /* output samples (stream, keyframe) per kernel launch; calls take any number */
 
 /* Library ABI version (major*1000 + minor). */
 int tf_version(void);
@@ -55,6 +55,17 @@ int tf_unit_rows(const void* x, int x_is_f32, int64_t rows, int dim, int64_t x_r
  *   out_f16      device [rows, dim] fp16 contiguous;  dim <= 1280 */
 int tf_layernorm_unit_rows(const void* x_f16, int64_t rows, int dim, int64_t x_row_stride, const float* gamma,
                            const float* beta, float eps, void* out_f16, tf_stream_t stream);
+
+/* norm1 of the PIVOTAL pass fused with both of its consumers (tokenflow_utils.py:323 -> :120-122 and
+ * :326-327 + util.py:66-67): one read of hidden_states produces
+ *   y_out     fp16(LN(x)) for every row — the operand autocast would cast for the to_q/to_k/to_v GEMMs
+ *   unit_out  fp16(LN(x) / ||LN(x)||_2) for the first `unit_rows` rows (the source-stream samples: the
+ *             pivot features the NN field correlates), from the unrounded fp32 LN like the reference
+ * Either output may be NULL.  Outputs may be strided (packed all-gather buffers): row pitch in elements,
+ * multiple of 8.  dim <= 1280. */
+int tf_layernorm_rows(const void* x_f16, int64_t rows, int dim, int64_t x_row_stride, const float* gamma,
+                      const float* beta, float eps, void* y_out_f16, int64_t y_row_stride, void* unit_out_f16,
+                      int64_t unit_row_stride, int64_t unit_rows, tf_stream_t stream);
 
 /* Token nearest-neighbour field.  Replaces tokenflow_utils.py:329-348 (+ util.py:68 `x @ y.T`,
  * fp16 output under autocast, and the two argmax reductions :340-343):
@@ -100,6 +111,28 @@ int tf_ext_attn_fwd_table(const void* q, int q_slabs, int64_t q_tok_stride, cons
                           const int32_t* q_slab, const int32_t* k_slab0, const int32_t* v_slab0,
                           const int32_t* n_kv, int S, int heads, int d, float scale, void* out,
                           tf_stream_t stream);
+
+/* Classifier-free guidance + DDIM update (eta = 0) of one denoising step, one pass over the latents.
+ * Replaces run_tokenflow_pnp.py:213-217 (`u + g*(c - u)`, `scheduler.step(...)['prev_sample']`), with the
+ * fp16 rounding sequence of the eager expression (bit-identical results).
+ *   eps_uncond, eps_cond, x, out   device [n] fp16 contiguous (x = the latents being denoised)
+ *   coef   device [4] fp32: sqrt(1-alpha_t), 1/sqrt(alpha_t), sqrt(alpha_prev), sqrt(1-alpha_prev) — in
+ *          device memory so a captured CUDA graph of the step replays for every timestep */
+int tf_cfg_ddim(const void* eps_uncond, const void* eps_cond, const void* x, const float* coef, float guidance,
+                int64_t n, void* out, tf_stream_t stream);
+
+/* ---- multi-GPU: all-gather of keyframe tensors along the pivotal-sample axis ----
+ * NCCL (all-gather over NVLink 5 / NVSwitch) bound at run time; one communicator per process/GPU.
+ * Rendezvous: rank 0 calls tf_comm_unique_id and ships the TF_COMM_ID_BYTES to the other ranks by any
+ * channel (the Python host uses a torch.distributed broadcast); every rank then calls tf_comm_init.
+ * tf_allgather enqueues on `stream` (CUDA-graph capturable): recv = [nranks][bytes_per_rank]. */
+#define TF_COMM_ID_BYTES 128
+typedef void* tf_comm_t;
+int tf_comm_nccl_version(void);                 /* NCCL version code, 0 if NCCL cannot be loaded */
+int tf_comm_unique_id(void* id_out);
+int tf_comm_init(const void* id, int nranks, int rank, tf_comm_t* comm_out);
+int tf_allgather(tf_comm_t comm, const void* send, void* recv, int64_t bytes_per_rank, tf_stream_t stream);
+int tf_comm_destroy(tf_comm_t comm);
 
 #ifdef __cplusplus
 }

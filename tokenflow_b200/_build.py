@@ -19,7 +19,8 @@ CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libtokenflow_b200.so"
 STAMP = PKG_DIR / ".libtokenflow_b200.stamp"
 
-SOURCES = ["tf_capi.cu", "tf_unit_rows.cu", "tf_propagate.cu", "tf_nn_field.cu", "tf_ext_attn.cu"]
+SOURCES = ["tf_capi.cu", "tf_unit_rows.cu", "tf_propagate.cu", "tf_nn_field.cu", "tf_ext_attn.cu", "tf_cfg_ddim.cu",
+           "tf_comm.cu"]
 HEADERS = ["tf_common.cuh", "tf_kernels.h", "../../include/tokenflow_b200.h"]
 
 NVCC_FLAGS = [

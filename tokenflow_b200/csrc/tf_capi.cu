@@ -1,8 +1,10 @@
 // C-ABI layer (include/tokenflow_b200.h): argument validation, per-frame tables, error plumbing.
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "../../include/tokenflow_b200.h"
 #include "tf_common.cuh"
@@ -136,45 +138,113 @@ int tf_layernorm_unit_rows(const void* x_f16, int64_t rows, int dim, int64_t x_r
   return e;
 }
 
+int tf_layernorm_rows(const void* x_f16, int64_t rows, int dim, int64_t x_row_stride, const float* gamma,
+                      const float* beta, float eps, void* y_out_f16, int64_t y_row_stride, void* unit_out_f16,
+                      int64_t unit_row_stride, int64_t unit_rows, tf_stream_t stream) {
+  if (rows < 0 || dim <= 0 || (dim & 7) || (x_row_stride & 7) || x_row_stride < dim ||
+      (y_out_f16 && ((y_row_stride & 7) || y_row_stride < dim)) ||
+      (unit_out_f16 && ((unit_row_stride & 7) || unit_row_stride < dim)) || unit_rows < 0) {
+    set_last_error("tf_layernorm_rows: bad shape rows=%lld dim=%d strides=(%lld,%lld,%lld) (multiples of 8 required)",
+                   (long long)rows, dim, (long long)x_row_stride, (long long)y_row_stride, (long long)unit_row_stride);
+    return TF_ERR_INVALID_ARGUMENT;
+  }
+  if (rows == 0) return TF_OK;
+  if (!x_f16 || !gamma || !beta || !aligned16(x_f16) || !aligned16(gamma) || !aligned16(beta) ||
+      (y_out_f16 && !aligned16(y_out_f16)) || (unit_out_f16 && !aligned16(unit_out_f16))) {
+    set_last_error("tf_layernorm_rows: NULL or misaligned pointer");
+    return TF_ERR_INVALID_ARGUMENT;
+  }
+  if (!y_out_f16 && (!unit_out_f16 || unit_rows == 0)) return TF_OK;
+  int e = launch_layernorm_rows(x_f16, rows, dim, x_row_stride, gamma, beta, eps, y_out_f16, y_row_stride,
+                                unit_out_f16, unit_row_stride, unit_rows, static_cast<cudaStream_t>(stream));
+  if (!e) g_launches += 1;
+  return e;
+}
+
+int tf_cfg_ddim(const void* eps_uncond, const void* eps_cond, const void* x, const float* coef, float guidance,
+                int64_t n, void* out, tf_stream_t stream) {
+  if (n < 0) { set_last_error("tf_cfg_ddim: n=%lld", (long long)n); return TF_ERR_INVALID_ARGUMENT; }
+  if (n == 0) return TF_OK;
+  if (!eps_uncond || !eps_cond || !x || !coef || !out || !aligned16(eps_uncond) || !aligned16(eps_cond) ||
+      !aligned16(x) || !aligned16(out)) {
+    set_last_error("tf_cfg_ddim: NULL or misaligned pointer");
+    return TF_ERR_INVALID_ARGUMENT;
+  }
+  int e = launch_cfg_ddim(eps_uncond, eps_cond, x, coef, guidance, n, out, static_cast<cudaStream_t>(stream));
+  if (!e) g_launches += 1;
+  return e;
+}
+
 int tf_nn_field(const void* x_unit, const void* piv_unit, const int32_t* kf_a, const int32_t* kf_b, int F, int S,
                 int dim, int K, int32_t* idx_a, int32_t* idx_b, tf_stream_t stream) {
-  if (S < 0 || dim <= 0 || (dim & 7) || K <= 0) {
+  if (F < 0 || S < 0 || dim <= 0 || (dim & 7) || K <= 0) {
     set_last_error("tf_nn_field: bad shape F=%d S=%d dim=%d K=%d", F, S, dim, K);
     return TF_ERR_INVALID_ARGUMENT;
   }
-  FrameTable tab;
-  if (int e = fill_table(tab, kf_a, kf_b, nullptr, F, K, "tf_nn_field")) return e;
+  if (F > 0 && !kf_a) { set_last_error("tf_nn_field: kf_a is NULL"); return TF_ERR_INVALID_ARGUMENT; }
+  // validate every chunk before the first launch
+  for (int f0 = 0; f0 < F; f0 += kMaxFrames) {
+    FrameTable tab;
+    const int fc = F - f0 < kMaxFrames ? F - f0 : kMaxFrames;
+    if (int e = fill_table(tab, kf_a + f0, kf_b ? kf_b + f0 : nullptr, nullptr, fc, K, "tf_nn_field")) return e;
+  }
   if (F == 0 || S == 0) return TF_OK;
-  if (!x_unit || !piv_unit || !idx_a || !aligned16(x_unit) || !aligned16(piv_unit)) {
+  bool need_b = false;
+  if (kf_b) for (int f = 0; f < F; ++f) need_b |= kf_b[f] >= 0;
+  if (!x_unit || !piv_unit || !idx_a || (need_b && !idx_b) || !aligned16(x_unit) || !aligned16(piv_unit)) {
     set_last_error("tf_nn_field: NULL or misaligned pointer");
     return TF_ERR_INVALID_ARGUMENT;
   }
-  int e = launch_nn_field(x_unit, piv_unit, tab, F, S, dim, K, idx_a, idx_b, static_cast<cudaStream_t>(stream));
-  if (!e) g_launches += 1;
-  return e;
+  const __half* xu = static_cast<const __half*>(x_unit);
+  for (int f0 = 0; f0 < F; f0 += kMaxFrames) {         // any number of frames: kMaxFrames per launch
+    FrameTable tab;
+    const int fc = F - f0 < kMaxFrames ? F - f0 : kMaxFrames;
+    fill_table(tab, kf_a + f0, kf_b ? kf_b + f0 : nullptr, nullptr, fc, K, "tf_nn_field");
+    const long long off = (long long)f0 * S;
+    int e = launch_nn_field(xu + off * dim, piv_unit, tab, fc, S, dim, K, idx_a + off, idx_b ? idx_b + off : nullptr,
+                            static_cast<cudaStream_t>(stream));
+    if (e) return e;
+    g_launches += 1;
+  }
+  return TF_OK;
 }
 
 int tf_propagate(const void* A, const int32_t* idx_a, const int32_t* idx_b, const int32_t* kf_a,
                  const int32_t* kf_b, const float* w, int F, int S, int dim, int K, const void* residual,
                  void* out, int out_is_f32, tf_stream_t stream) {
-  if (S < 0 || dim <= 0 || (dim & 7) || K <= 0) {
+  if (F < 0 || S < 0 || dim <= 0 || (dim & 7) || K <= 0) {
     set_last_error("tf_propagate: bad shape F=%d S=%d dim=%d K=%d", F, S, dim, K);
     return TF_ERR_INVALID_ARGUMENT;
   }
-  FrameTable tab;
-  if (int e = fill_table(tab, kf_a, kf_b, w, F, K, "tf_propagate")) return e;
-  if (F == 0 || S == 0) return TF_OK;
+  if (F > 0 && !kf_a) { set_last_error("tf_propagate: kf_a is NULL"); return TF_ERR_INVALID_ARGUMENT; }
   bool need_b = false;
-  for (int f = 0; f < F; ++f) need_b |= tab.kf_b[f] >= 0;
+  for (int f0 = 0; f0 < F; f0 += kMaxFrames) {
+    FrameTable tab;
+    const int fc = F - f0 < kMaxFrames ? F - f0 : kMaxFrames;
+    if (int e = fill_table(tab, kf_a + f0, kf_b ? kf_b + f0 : nullptr, w ? w + f0 : nullptr, fc, K, "tf_propagate"))
+      return e;
+    for (int f = 0; f < fc; ++f) need_b |= tab.kf_b[f] >= 0;
+  }
+  if (F == 0 || S == 0) return TF_OK;
   if (!A || !idx_a || !out || (need_b && (!idx_b || !w)) || !aligned16(A) || !aligned16(out) ||
       (residual && !aligned16(residual))) {
     set_last_error("tf_propagate: NULL or misaligned pointer");
     return TF_ERR_INVALID_ARGUMENT;
   }
-  int e = launch_propagate(A, idx_a, idx_b, tab, F, S, dim, K, residual, out, out_is_f32,
-                           static_cast<cudaStream_t>(stream));
-  if (!e) g_launches += 1;
-  return e;
+  const size_t out_esz = out_is_f32 ? 4 : 2;
+  for (int f0 = 0; f0 < F; f0 += kMaxFrames) {         // any number of frames: kMaxFrames per launch, no copies
+    FrameTable tab;
+    const int fc = F - f0 < kMaxFrames ? F - f0 : kMaxFrames;
+    fill_table(tab, kf_a + f0, kf_b ? kf_b + f0 : nullptr, w ? w + f0 : nullptr, fc, K, "tf_propagate");
+    const long long off = (long long)f0 * S;
+    int e = launch_propagate(A, idx_a + off, idx_b ? idx_b + off : nullptr, tab, fc, S, dim, K,
+                             residual ? static_cast<const __half*>(residual) + off * dim : nullptr,
+                             static_cast<char*>(out) + (size_t)off * dim * out_esz, out_is_f32, F,
+                             static_cast<cudaStream_t>(stream));
+    if (e) return e;
+    g_launches += 1;
+  }
+  return TF_OK;
 }
 
 int tf_ext_attn_fwd_table(const void* q, int q_slabs, int64_t q_tok_stride, const void* k, const void* v,
@@ -182,7 +252,7 @@ int tf_ext_attn_fwd_table(const void* q, int q_slabs, int64_t q_tok_stride, cons
                           const int32_t* q_slab, const int32_t* k_slab0, const int32_t* v_slab0,
                           const int32_t* n_kv, int S, int heads, int d, float scale, void* out,
                           tf_stream_t stream) {
-  if (n_out < 0 || n_out > kMaxAttnSamples || S < 0 || heads <= 0 || d <= 0 || (d & 7) ||
+  if (n_out < 0 || S < 0 || heads <= 0 || d <= 0 || (d & 7) ||
       q_tok_stride < (int64_t)heads * d || kv_tok_stride < (int64_t)heads * d || (q_tok_stride & 7) ||
       (kv_tok_stride & 7)) {
     set_last_error("tf_ext_attn: bad shape n_out=%d S=%d heads=%d d=%d strides=(%lld,%lld)", n_out, S, heads, d,
@@ -195,46 +265,47 @@ int tf_ext_attn_fwd_table(const void* q, int q_slabs, int64_t q_tok_stride, cons
     set_last_error("tf_ext_attn: NULL or misaligned pointer");
     return TF_ERR_INVALID_ARGUMENT;
   }
-  // heavy samples (most key slabs) first: the hardware block scheduler then fills the tail of the
-  // grid with the cheap own-frame (source stream) samples
-  AttnTable tab;
-  memset(&tab, 0, sizeof(tab));
-  int order[kMaxAttnSamples];
-  for (int i = 0; i < n_out; ++i) order[i] = i;
-  for (int i = 1; i < n_out; ++i) {   // stable insertion sort by n_kv descending
-    int x = order[i], j = i - 1;
-    while (j >= 0 && n_kv[order[j]] < n_kv[x]) { order[j + 1] = order[j]; --j; }
-    order[j + 1] = x;
-  }
-  for (int slot = 0; slot < n_out; ++slot) {
-    const int i = order[slot];
+  for (int i = 0; i < n_out; ++i) {
     if (q_slab[i] < 0 || q_slab[i] >= q_slabs || n_kv[i] <= 0 || k_slab0[i] < 0 || v_slab0[i] < 0 ||
         k_slab0[i] + n_kv[i] > kv_slabs || v_slab0[i] + n_kv[i] > kv_slabs || out_slab[i] < 0) {
       set_last_error("tf_ext_attn: sample %d has an out-of-range slab (q=%d k0=%d v0=%d n_kv=%d)", i, q_slab[i],
                      k_slab0[i], v_slab0[i], n_kv[i]);
       return TF_ERR_INVALID_ARGUMENT;
     }
-    tab.s[slot].out_sample = out_slab[i];
-    tab.s[slot].q_sample = q_slab[i];
-    tab.s[slot].k_sample0 = k_slab0[i];
-    tab.s[slot].v_sample0 = v_slab0[i];
-    tab.s[slot].n_kv = n_kv[i];
   }
-  int e = launch_ext_attn(q, k, v, q_tok_stride, kv_tok_stride, q_slabs, kv_slabs, tab, n_out, S, heads, d, scale,
-                          out, static_cast<cudaStream_t>(stream));
-  if (!e) g_launches += 1;
-  return e;
+  // heavy samples (most key slabs) first: the hardware block scheduler then fills the tail of the
+  // grid with the cheap own-frame (source stream) samples
+  std::vector<int> order(n_out);
+  for (int i = 0; i < n_out; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return n_kv[a] > n_kv[b]; });
+  for (int s0 = 0; s0 < n_out; s0 += kMaxAttnSamples) {       // any number of samples: kMaxAttnSamples per launch
+    const int nc = n_out - s0 < kMaxAttnSamples ? n_out - s0 : kMaxAttnSamples;
+    AttnTable tab;
+    memset(&tab, 0, sizeof(tab));
+    for (int slot = 0; slot < nc; ++slot) {
+      const int i = order[s0 + slot];
+      tab.s[slot].out_sample = out_slab[i];
+      tab.s[slot].q_sample = q_slab[i];
+      tab.s[slot].k_sample0 = k_slab0[i];
+      tab.s[slot].v_sample0 = v_slab0[i];
+      tab.s[slot].n_kv = n_kv[i];
+    }
+    int e = launch_ext_attn(q, k, v, q_tok_stride, kv_tok_stride, q_slabs, kv_slabs, tab, nc, S, heads, d, scale, out,
+                            static_cast<cudaStream_t>(stream));
+    if (e) return e;
+    g_launches += 1;
+  }
+  return TF_OK;
 }
 
 int tf_ext_attn_fwd(const void* q, const void* k, const void* v, int64_t tok_stride, int n_frames, int S,
                     int heads, int d, float scale, int inject, void* out, tf_stream_t stream) {
   const int n = n_frames;
-  if (n < 0 || 3 * n > kMaxAttnSamples) {
-    set_last_error("tf_ext_attn_fwd: n_frames=%d outside [0,%d]", n, kMaxAttnSamples / 3);
+  if (n < 0) {
+    set_last_error("tf_ext_attn_fwd: n_frames=%d", n);
     return TF_ERR_INVALID_ARGUMENT;
   }
-  int32_t out_slab[kMaxAttnSamples], q_slab[kMaxAttnSamples], k0[kMaxAttnSamples], v0[kMaxAttnSamples],
-      nkv[kMaxAttnSamples];
+  std::vector<int32_t> out_slab(3 * n), q_slab(3 * n), k0(3 * n), v0(3 * n), nkv(3 * n);
   for (int s = 0; s < 3; ++s) {
     for (int f = 0; f < n; ++f) {
       const int i = s * n + f;
@@ -249,8 +320,8 @@ int tf_ext_attn_fwd(const void* q, const void* k, const void* v, int64_t tok_str
       }
     }
   }
-  return tf_ext_attn_fwd_table(q, 3 * n, tok_stride, k, v, 3 * n, tok_stride, 3 * n, out_slab, q_slab, k0, v0, nkv, S,
-                               heads, d, scale, out, stream);
+  return tf_ext_attn_fwd_table(q, 3 * n, tok_stride, k, v, 3 * n, tok_stride, 3 * n, out_slab.data(), q_slab.data(),
+                               k0.data(), v0.data(), nkv.data(), S, heads, d, scale, out, stream);
 }
 
 }  // extern "C"

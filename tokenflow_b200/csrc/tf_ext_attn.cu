@@ -345,6 +345,8 @@ ext_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 // TMEM: score buffers [0,256), O_A [256,320), O_B [320,384)
 // ================================================================================================
 constexpr int kPPStagesMax = 12;
+constexpr bool kDefaultOnes = true;        // measured choices (profiles/r02_ext_attn_variants.md)
+constexpr int kDefaultPolyOnes = 0, kDefaultPoly = 0;
 struct AttnCtl2 {
   uint64_t q_full;
   uint64_t kv_full[kPPStagesMax];
@@ -355,10 +357,31 @@ struct AttnCtl2 {
                              // warps that share a sub-partition (and therefore its MUFU)
   uint64_t pv_done[2][2];    // [tile X][t & 1]: two alternating barriers, so a softmax warp that runs two
                              // tiles ahead of the tensor pipe can still name "P V of tile t" unambiguously
+  uint64_t v_ready[kPPStagesMax];   // kOnes: the V tile of this stage carries its column of ones (warp 3)
   uint32_t tmem_base;
 };
 
-template <int kBlockN>
+// 2^x for x <= ~2^8 on the FMA/ALU pipes (no MUFU): Cody-Waite split x = n + r with the round-to-nearest
+// magic constant, degree-3 minimax polynomial for 2^r on [-0.5, 0.5] (max relative error 1.0e-4, five times
+// below the fp16 rounding the probabilities get anyway), exponent inserted with one shift-add.
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -125.0f);                               // keeps the exponent arithmetic in range (and -inf -> ~0)
+  const float t = x + 12582912.0f;                     // 1.5 * 2^23: integer part of x in the low mantissa bits
+  const float r = x - (t - 12582912.0f);               // r in [-0.5, 0.5]
+  float p = fmaf(0.05500871315598488f, r, 0.24221068620681763f);
+  p = fmaf(p, r, 0.6932829022407532f);
+  p = fmaf(p, r, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+// which of 16 consecutive row elements take the polynomial: k of 16, evenly spread
+__host__ __device__ constexpr bool poly_slot(int e, int k16) { return ((e % 16 + 1) * k16) / 16 != ((e % 16) * k16) / 16; }
+
+// kPoly16: of every 16 probabilities, this many are evaluated with poly_exp2 instead of MUFU.EX2 (the exp2
+//          loop is MUFU-bound at small head dims; FA4-style split of the work over two pipes).
+// kOnes:   row sums by the tensor core — warp 3 writes 1.0 into the (zero padded) column d of every V tile, so
+//          column d of the O accumulator is sum_c P[:, c]; needs d % 16 != 0 (a free padding column inside the
+//          P V MMA's N).  Saves one FADD per probability on the FMA pipe that the polynomial needs.
+template <int kBlockN, int kPoly16, bool kOnes>
 __global__ void __launch_bounds__(384, 1)
 ext_attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                    const __grid_constant__ CUtensorMap map_v, const AttnTable tab, const AttnParams prm,
@@ -399,6 +422,7 @@ ext_attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     for (int i = 0; i < stages; ++i) {
       mbar_init(&ctl->kv_full[i], 1);
       mbar_init(&ctl->kv_empty[i], 2);
+      mbar_init(&ctl->v_ready[i], 1);
     }
     for (int x = 0; x < 2; ++x) {
       for (int b = 0; b < 2; ++b) {
@@ -417,6 +441,10 @@ ext_attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   tc_fence_after_sync();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);     // warp-uniform for the compiler
 
+  // register budgets: the 4 service warps (TMA, 2 MMA issuers, ones writer) need few registers, the 8 softmax
+  // warps hold a 128-element score row each plus the polynomial's temporaries: 4*32*96 + 8*32*200 = 62 K registers
+  if (warp < 4) {
+  warpgroup_reg_dec<96>();
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
@@ -478,10 +506,12 @@ ext_attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       if (++qk_stage == stages) { qk_stage = 0; qk_phase ^= 1; }
     }
     int stage = 0;                                 // ring position of tile t (its V tile feeds P V)
+    uint32_t pv_phase = 0;
     for (int t = 0; t < T; ++t) {
       const int buf = t % kNBuf;                   // kNBuf is 1 or 2
       const bool refill = t + kNBuf < T;
       if (refill) mbar_wait(&ctl->kv_full[qk_stage], qk_phase);   // K tile of the refill, polled while idle anyway
+      if (kOnes) mbar_wait(&ctl->v_ready[stage], pv_phase);       // the V tile has its ones column
       if (X == 0 && lane_id() == 0) TF_TRACE_EV(2, t, 0);
       mbar_wait(&ctl->p_full[X][buf], (uint32_t)((t / kNBuf) & 1));
       tc_fence_after_sync();
@@ -498,10 +528,32 @@ ext_attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       }
       __syncwarp();
       if (X == 0 && lane_id() == 0) TF_TRACE_EV(2, t, 3);
-      if (++stage == stages) stage = 0;
+      if (++stage == stages) { stage = 0; pv_phase ^= 1; }
       if (refill && ++qk_stage == stages) { qk_stage = 0; qk_phase ^= 1; }
     }
-  } else if (warp >= 4) {              // (warp 3 is a spare: it keeps the softmax warps aligned to TMEM lane quadrants)
+  } else if (warp == 3) {
+    // ===================== ones column (kOnes): V[:, d] = 1 so that O[:, d] accumulates the row sums ============
+    if constexpr (kOnes) {
+      const uint32_t col_byte = (uint32_t)d * 2u;                 // d % 8 == 0: the column starts a 16-byte chunk or its half
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < T; ++t) {
+        mbar_wait(&ctl->kv_full[stage], phase);
+        uint8_t* vt = ring + stage * kStageBytes + kTileBytes;
+#pragma unroll
+        for (int r = (int)lane_id(); r < kBlockN; r += 32) {      // 128-byte swizzle: 16-byte chunk index ^ (row & 7)
+          const uint32_t off = (uint32_t)r * 128u + ((((col_byte >> 4) ^ ((uint32_t)r & 7u))) << 4) + (col_byte & 15u);
+          *reinterpret_cast<__half*>(vt + off) = __float2half_rn(1.0f);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(&ctl->v_ready[stage]);
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+  } else {                             // (warps 4..11 sit on TMEM lane quadrants warp % 4)
+    warpgroup_reg_inc<200>();
     // ===================== softmax warps: tile X = (warp - 4) / 4 =====================
     const int X = (warp - 4) >> 2;
     const int quad = warp & 3;
@@ -588,12 +640,14 @@ ext_attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           if (c < kChunks) {
-            v[c][2 * i] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(v[c][2 * i]), sl2, neg_m)));
-            v[c][2 * i + 1] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(v[c][2 * i + 1]), sl2, neg_m)));
+            const float x0 = fmaf(__uint_as_float(v[c][2 * i]), sl2, neg_m);
+            const float x1 = fmaf(__uint_as_float(v[c][2 * i + 1]), sl2, neg_m);
+            v[c][2 * i] = __float_as_uint(poly_slot(2 * i, kPoly16) ? poly_exp2(x0) : fast_exp2(x0));
+            v[c][2 * i + 1] = __float_as_uint(poly_slot(2 * i + 1, kPoly16) ? poly_exp2(x1) : fast_exp2(x1));
           }
           if (c > 0) {
             const float p0 = __uint_as_float(v[c - 1][2 * i]), p1 = __uint_as_float(v[c - 1][2 * i + 1]);
-            ls[i & 3] += p0 + p1;
+            if (!kOnes) ls[i & 3] += p0 + p1;
             pk[i] = pack_f16x2_rn(p0, p1);
           }
         }
@@ -615,6 +669,12 @@ ext_attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     // ---- final: O / L -> fp16 ----
     mbar_wait(&ctl->pv_done[X][(T - 1) & 1], (uint32_t)(((T - 1) >> 1) & 1));
     tc_fence_after_sync();
+    if (kOnes) {                                   // the row sum is column d of the accumulator (sum of the fp16 P)
+      uint32_t lsum;
+      tmem_ld1(o_addr + d, lsum);
+      tmem_wait_ld();
+      l_run = __uint_as_float(lsum);
+    }
     const float inv_l = 1.0f / l_run;
     const int p_tok = m0 + X * kBlockM + row;
     __half* orow = out + ((long long)smp.out_sample * S + p_tok) * prm.out_tok_stride + (long long)head * d;
@@ -646,7 +706,7 @@ ext_attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   }
 }
 
-template <int kBlockN>
+template <int kBlockN, int kPoly16, bool kOnes>
 int launch_pp(const void* q, const void* k, const void* v, long long q_tok_stride, long long kv_tok_stride,
               int q_samples_total, int kv_samples_total, const AttnTable& tab, int n_out, int S, int heads, int d,
               float scale, void* out, cudaStream_t stream) {
@@ -675,12 +735,403 @@ int launch_pp(const void* q, const void* k, const void* v, long long q_tok_strid
   prm.stages = stages;
   prm.scale_log2 = scale * 1.4426950408889634f;
   prm.out_tok_stride = (long long)heads * d;
-  auto kern = ext_attn_pp_kernel<kBlockN>;
+  auto kern = ext_attn_pp_kernel<kBlockN, kPoly16, kOnes>;
   if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes),
                  "tf_ext_attn smem attribute"))
     return TF_ERR_CUDA;
   const long long grid = (long long)n_out * heads * prm.tiles_m;
   kern<<<(unsigned)grid, 384, smem_bytes, stream>>>(map_q, map_k, map_v, tab, prm, static_cast<__half*>(out));
+  return check_cuda(cudaGetLastError(), "tf_ext_attn launch");
+}
+
+// ================================================================================================
+// Quad-stream kernel (head dim <= 64): two 128-query tiles per CTA x two 64-key halves of every key tile
+// = four independent online-softmax streams, 16 softmax warps (four per SM sub-partition).
+//
+// Why (profiles/r02_ext_attn_variants.md): in the ping-pong kernel one warp per sub-partition runs the exp2
+// phase at a time, and ONE warp cannot issue faster than about one instruction every three cycles — the
+// exp2 phase ran at 13-15 cycles per probability against a MUFU cost of 8.1, so neither the MUFU (68 %) nor
+// the tensor pipe (26 %) was busy, and moving exp2 work to the FMA pipe only lengthened the phase.  The
+// remedy is issue parallelism, not fewer MUFU operations:
+//   * every score row is split between two threads (keys 0-63 / 64-127 of the tile) in different warps;
+//     each half is its own flash-attention stream with its own running max, row sum and accumulator
+//     (O_XL, O_XR: the P V MMA's eight 16-key steps are simply issued as 4 + 4 into two accumulators), merged
+//     once at the end — no cross-thread traffic inside the loop, four warps per sub-partition in flight;
+//   * x * scale - max is evaluated two elements at a time with FFMA2 (packed fp32, sm_100);
+//   * row sums come from the tensor core (a column of ones in V, kOnes) so no FADD per probability;
+//   * a fraction of the exp2 (kPoly16 of 16) may go to the FMA pipe once the MUFU is the limiter.
+//   warp 0: TMA   warps 1,2: MMA issue for tile A / B   warp 3: ones column   warps 4-19: softmax (X, half, quadrant)
+// TMEM (512 columns): S_A [0,128)  S_B [128,256)  O_AL O_AR O_BL O_BR [256,512) in 64-column slots.
+// fp16 P_XL overwrites S_X columns [0,32), P_XR columns [64,96) (each half only overwrites scores it has read).
+// ================================================================================================
+struct AttnCtl4 {
+  uint64_t q_full;
+  uint64_t kv_full[kPPStagesMax];
+  uint64_t kv_empty[kPPStagesMax];
+  uint64_t v_ready[kPPStagesMax];
+  uint64_t s_full[2];          // [tile X]
+  uint64_t p_full[2][2];       // [tile X][half]
+  uint64_t pv_done[2][2][2];   // [tile X][half][t & 1]
+  uint64_t fin[2];             // [tile X]: the R half published its (max, sum) for the final merge
+  float2 ml_r[2][128];         // [tile X][row]: running max and row sum of the R half
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void ffma2(float& y0, float& y1, float a0, float a1, float b, float c) {
+  uint64_t ra, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a0), "f"(a1));
+  asm("{\n\t.reg .b64 rb, rc;\n\tmov.b64 rb, {%2, %2};\n\tmov.b64 rc, {%3, %3};\n\t"
+      "fma.rn.f32x2 %0, %1, rb, rc;\n\t}"
+      : "=l"(rd) : "l"(ra), "f"(b), "f"(c));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(y0), "=f"(y1) : "l"(rd));
+}
+
+template <int kPoly16, bool kOnes>
+__global__ void __launch_bounds__(640, 1)
+ext_attn_q4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                   const __grid_constant__ CUtensorMap map_v, const AttnTable tab, const AttnParams prm,
+                   __half* __restrict__ out) {
+  constexpr int kBlockN = 128;
+  constexpr int kQTileBytes = kBlockM * 128;
+  constexpr int kQBytes = 2 * kQTileBytes;
+  constexpr int kTileBytes = kBlockN * 128;
+  constexpr int kStageBytes = 2 * kTileBytes;
+  constexpr int kOCol = 256;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_smem = smem;
+  uint8_t* ring = smem + kQBytes;
+  AttnCtl4* ctl = reinterpret_cast<AttnCtl4*>(ring + prm.stages * kStageBytes);
+
+  const int S = prm.S, d = prm.d, stages = prm.stages;
+  const int per_sample = prm.heads * prm.tiles_m;              // tiles_m = 256-query tile pairs
+  const int sample_slot = blockIdx.x / per_sample;
+  const int rem = blockIdx.x - sample_slot * per_sample;
+  const int head = rem / prm.tiles_m;
+  const int m0 = (rem - head * prm.tiles_m) * (2 * kBlockM);
+  const AttnSample smp = tab.s[sample_slot];
+  const int tiles_per_slab = (S + kBlockN - 1) / kBlockN;
+  const int T = smp.n_kv * tiles_per_slab;
+  const int ksteps = (d + 15) / 16;
+  const int n_pv = ((d + 15) / 16) * 16;
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_v);
+    mbar_init(&ctl->q_full, 1);
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&ctl->kv_full[i], 1);
+      mbar_init(&ctl->kv_empty[i], 2);
+      mbar_init(&ctl->v_ready[i], 1);
+    }
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(&ctl->s_full[x], 1);
+      mbar_init(&ctl->fin[x], 4);
+      for (int hh = 0; hh < 2; ++hh) {
+        mbar_init(&ctl->p_full[x][hh], 4);
+        mbar_init(&ctl->pv_done[x][hh][0], 1);
+        mbar_init(&ctl->pv_done[x][hh][1], 1);
+      }
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&ctl->tmem_base, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
+
+  if (warp < 4) {
+    warpgroup_reg_dec<64>();
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&ctl->q_full, (uint32_t)kQBytes);
+        tma_load_4d(q_smem, &map_q, &ctl->q_full, 0, head, m0, smp.q_sample);
+        tma_load_4d(q_smem + kQTileBytes, &map_q, &ctl->q_full, 0, head, m0 + kBlockM, smp.q_sample);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = 0; t < T; ++t) {
+          const int slab = t / tiles_per_slab;
+          const int n0 = (t - slab * tiles_per_slab) * kBlockN;
+          mbar_wait(&ctl->kv_empty[stage], phase ^ 1);
+          uint8_t* st = ring + stage * kStageBytes;
+          mbar_arrive_expect_tx(&ctl->kv_full[stage], (uint32_t)kStageBytes);
+          tma_load_4d(st, &map_k, &ctl->kv_full[stage], 0, head, n0, smp.k_sample0 + slab);
+          tma_load_4d(st + kTileBytes, &map_v, &ctl->kv_full[stage], 0, head, n0, smp.v_sample0 + slab);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1 || warp == 2) {
+      // ===================== MMA issuers: one warp per query tile (warp 1 -> A, warp 2 -> B) ==============
+      const int X = warp - 1;
+      const uint32_t idesc_qk = umma_idesc_f16(128, kBlockN, 0);
+      const uint32_t idesc_pv = umma_idesc_f16(128, (uint32_t)n_pv, 1);
+      constexpr uint32_t hi_kmaj = umma_desc_hi(1024);
+      const uint32_t q_lo = umma_desc_lo(smem_u32(q_smem + X * kQTileBytes), 16);
+      const uint32_t ring_k_lo = umma_desc_lo(smem_u32(ring), 16);
+      const uint32_t ring_v_lo = umma_desc_lo(smem_u32(ring + kTileBytes), kTileBytes);
+      constexpr uint32_t kStageStep = kStageBytes >> 4;
+      const uint32_t s_tmem = tmem_base + (uint32_t)(X * kBlockN);
+      const uint32_t o_l = tmem_base + kOCol + (uint32_t)(X * 2) * 64;
+      const uint32_t o_r = o_l + 64;
+      auto issue_qk = [&](int st) {
+        const uint32_t k_lo = ring_k_lo + (uint32_t)st * kStageStep;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          if (ks < ksteps) tc_mma_ss_lh(s_tmem, q_lo + ks * 2, hi_kmaj, k_lo + ks * 2, hi_kmaj, idesc_qk, ks > 0 ? 1u : 0u);
+        tc_commit(&ctl->s_full[X]);
+      };
+      mbar_wait(&ctl->q_full, 0);
+      // tile B starts once the first half of tile A's first probabilities exists: staggers the streams
+      if (X == 1) mbar_wait(&ctl->p_full[0][0], 0);
+      int qk_stage = 0;
+      uint32_t qk_phase = 0;
+      mbar_wait(&ctl->kv_full[0], 0);
+      tc_fence_after_sync();
+      if (elect_one()) issue_qk(0);
+      __syncwarp();
+      if (++qk_stage == stages) { qk_stage = 0; qk_phase ^= 1; }
+      int stage = 0;
+      uint32_t pv_phase = 0;
+      for (int t = 0; t < T; ++t) {
+        const bool refill = t + 1 < T;
+        const uint32_t par = (uint32_t)(t & 1);
+        if (refill) mbar_wait(&ctl->kv_full[qk_stage], qk_phase);
+        if (kOnes) mbar_wait(&ctl->v_ready[stage], pv_phase);
+        const uint32_t v_lo = ring_v_lo + (uint32_t)stage * kStageStep;
+        mbar_wait(&ctl->p_full[X][0], par);
+        tc_fence_after_sync();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)                 // O_XL (+)= P_X[:, keys 16k..16k+15] V[16k.., :]
+            tc_mma_ts_lh(o_l, s_tmem + k * 8, v_lo + k * 128, hi_kmaj, idesc_pv, (t > 0 || k > 0) ? 1u : 0u);
+          tc_commit(&ctl->pv_done[X][0][par]);
+        }
+        __syncwarp();
+        mbar_wait(&ctl->p_full[X][1], par);
+        tc_fence_after_sync();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)                 // O_XR (+)= P_X[:, keys 64+16k..] V[64+16k.., :]
+            tc_mma_ts_lh(o_r, s_tmem + 64 + k * 8, v_lo + (4 + k) * 128, hi_kmaj, idesc_pv, (t > 0 || k > 0) ? 1u : 0u);
+          tc_commit(&ctl->pv_done[X][1][par]);
+          tc_commit(&ctl->kv_empty[stage]);
+          if (refill) issue_qk(qk_stage);             // both halves of P_X are consumed in order before S_X is rewritten
+        }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; pv_phase ^= 1; }
+        if (refill && ++qk_stage == stages) { qk_stage = 0; qk_phase ^= 1; }
+      }
+    } else {
+      // ===================== ones column (kOnes): V[:, d] = 1 so that O[:, d] accumulates the row sums ============
+      if constexpr (kOnes) {
+        const uint32_t col_byte = (uint32_t)d * 2u;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = 0; t < T; ++t) {
+          mbar_wait(&ctl->kv_full[stage], phase);
+          uint8_t* vt = ring + stage * kStageBytes + kTileBytes;
+#pragma unroll
+          for (int r = (int)lane_id(); r < kBlockN; r += 32) {
+            const uint32_t off = (uint32_t)r * 128u + ((((col_byte >> 4) ^ ((uint32_t)r & 7u))) << 4) + (col_byte & 15u);
+            *reinterpret_cast<__half*>(vt + off) = __float2half_rn(1.0f);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane_id() == 0) mbar_arrive(&ctl->v_ready[stage]);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    warpgroup_reg_inc<104>();
+    // ===================== softmax streams: (tile X, key half H, lane quadrant) =====================
+    const int sid = warp - 4;
+    const int X = sid >> 3;
+    const int H = (sid >> 2) & 1;
+    const int quad = warp & 3;
+    const int row = quad * 32 + (int)lane_id();
+    const uint32_t t_lane = (uint32_t)(quad * 32) << 16;
+    const uint32_t s_addr = tmem_base + t_lane + (uint32_t)(X * kBlockN + H * 64);     // own 64 score columns; P at their start
+    const uint32_t o_addr = tmem_base + t_lane + kOCol + (uint32_t)(X * 2 + H) * 64;
+    const float sl2 = prm.scale_log2;
+    float m_run = 0.f;
+    float l_run = 0.f;
+    int slab_tile = 0;
+    for (int t = 0; t < T; ++t) {
+      const int valid = min(64, S - slab_tile * kBlockN - H * 64);          // key columns of this half inside the slab
+      if (++slab_tile == tiles_per_slab) slab_tile = 0;
+      mbar_wait(&ctl->s_full[X], (uint32_t)(t & 1));
+      tc_fence_after_sync();
+      uint32_t v[2][32];
+      tmem_ld32(s_addr, v[0]);
+      tmem_ld32(s_addr + 32, v[1]);
+      tmem_wait_ld();
+      if (valid < 64) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (32 * c + i >= valid) v[c][i] = 0xFF800000u;
+      }
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          mx[0] = fmax3(mx[0], __uint_as_float(v[c][i + 0]), __uint_as_float(v[c][i + 1]));
+          mx[1] = fmax3(mx[1], __uint_as_float(v[c][i + 2]), __uint_as_float(v[c][i + 3]));
+          mx[2] = fmax3(mx[2], __uint_as_float(v[c][i + 4]), __uint_as_float(v[c][i + 5]));
+          mx[3] = fmax3(mx[3], __uint_as_float(v[c][i + 6]), __uint_as_float(v[c][i + 7]));
+        }
+      // a fully masked half tile (ragged last tile) has max = -inf: keep the running max finite
+      const float mt_s = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sl2, -1.0e30f);
+      if (t == 0) {
+        m_run = mt_s;
+      } else {
+        const bool need = mt_s > m_run + kRescaleThreshold;
+        if (__any_sync(0xffffffffu, need)) {
+          mbar_wait(&ctl->pv_done[X][H][(t - 1) & 1], (uint32_t)(((t - 1) >> 1) & 1));
+          tc_fence_after_sync();
+          const float m_new = fmaxf(m_run, mt_s);
+          const float alpha = fast_exp2(m_run - m_new);
+          m_run = m_new;
+          l_run *= alpha;
+          for (int c0 = 0; c0 < n_pv; c0 += 16) {
+            uint32_t o[16];
+            tmem_ld16(o_addr + c0, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(o_addr + c0, o);
+          }
+          tmem_wait_st();
+        }
+      }
+      const float neg_m = -m_run;
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c <= 2; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (c < 2) {
+            float x0, x1;
+            ffma2(x0, x1, __uint_as_float(v[c][2 * i]), __uint_as_float(v[c][2 * i + 1]), sl2, neg_m);
+            v[c][2 * i] = __float_as_uint(poly_slot(2 * i, kPoly16) ? poly_exp2(x0) : fast_exp2(x0));
+            v[c][2 * i + 1] = __float_as_uint(poly_slot(2 * i + 1, kPoly16) ? poly_exp2(x1) : fast_exp2(x1));
+          }
+          if (c > 0) {
+            const float p0 = __uint_as_float(v[c - 1][2 * i]), p1 = __uint_as_float(v[c - 1][2 * i + 1]);
+            if (!kOnes) ls[i & 3] += p0 + p1;
+            pk[i] = pack_f16x2_rn(p0, p1);
+          }
+        }
+        if (c > 0) tmem_st16(s_addr + 16 * (c - 1), pk);
+      }
+      if (!kOnes) l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      tmem_wait_st();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&ctl->p_full[X][H]);
+    }
+    // ---- final merge of the two key halves of a row, O / L -> fp16 ----
+    mbar_wait(&ctl->pv_done[X][H][(T - 1) & 1], (uint32_t)(((T - 1) >> 1) & 1));
+    tc_fence_after_sync();
+    if (kOnes) {
+      uint32_t lsum;
+      tmem_ld1(o_addr + d, lsum);
+      tmem_wait_ld();
+      l_run = __uint_as_float(lsum);
+    }
+    if (H == 1) {
+      ctl->ml_r[X][row] = make_float2(m_run, l_run);
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&ctl->fin[X]);
+    } else {
+      mbar_wait(&ctl->pv_done[X][1][(T - 1) & 1], (uint32_t)(((T - 1) >> 1) & 1));     // O_XR complete
+      mbar_wait(&ctl->fin[X], 0);
+      tc_fence_after_sync();
+      const float2 mr = ctl->ml_r[X][row];
+      const float m = fmaxf(m_run, mr.x);
+      const float a_l = fast_exp2(m_run - m), a_r = fast_exp2(mr.x - m);
+      const float inv_l = 1.0f / (a_l * l_run + a_r * mr.y);
+      const float w_l = a_l * inv_l, w_r = a_r * inv_l;
+      const int p_tok = m0 + X * kBlockM + row;
+      __half* orow = out + ((long long)smp.out_sample * S + p_tok) * prm.out_tok_stride + (long long)head * d;
+      for (int c0 = 0; c0 < n_pv; c0 += 16) {
+        uint32_t ol[16], orr[16];
+        tmem_ld16(o_addr + c0, ol);
+        tmem_ld16(o_addr + 64 + c0, orr);
+        tmem_wait_ld();
+        if (p_tok < S) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            if (c0 + g * 8 < d) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                f[e] = fmaf(w_l, __uint_as_float(ol[g * 8 + e]), w_r * __uint_as_float(orr[g * 8 + e]));
+              uint4 w;
+              w.x = pack_f16x2_rn(f[0], f[1]);
+              w.y = pack_f16x2_rn(f[2], f[3]);
+              w.z = pack_f16x2_rn(f[4], f[5]);
+              w.w = pack_f16x2_rn(f[6], f[7]);
+              *reinterpret_cast<uint4*>(orow + c0 + g * 8) = w;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int kPoly16, bool kOnes>
+int launch_q4(const void* q, const void* k, const void* v, long long q_tok_stride, long long kv_tok_stride,
+              int q_samples_total, int kv_samples_total, const AttnTable& tab, int n_out, int S, int heads, int d,
+              float scale, void* out, cudaStream_t stream) {
+  constexpr int kBlockN = 128;
+  constexpr int kQBytes = 2 * kBlockM * 128, kStageBytes = 2 * kBlockN * 128;
+  int stages = (227 * 1024 - 1024 - (int)sizeof(AttnCtl4) - 64 - kQBytes) / kStageBytes;
+  if (stages > kPPStagesMax) stages = kPPStagesMax;
+  const size_t smem_bytes = 1024 + kQBytes + (size_t)stages * kStageBytes + sizeof(AttnCtl4);
+  CUtensorMap map_q, map_k, map_v;
+  auto make = [&](CUtensorMap* m, const void* base, long long tok_stride, int samples, int box_rows) -> int {
+    const uint64_t dims[4] = {(uint64_t)d, (uint64_t)heads, (uint64_t)S, (uint64_t)samples};
+    const uint64_t strides[3] = {(uint64_t)d * 2, (uint64_t)tok_stride * 2, (uint64_t)S * tok_stride * 2};
+    const uint32_t box[4] = {64, 1, (uint32_t)box_rows, 1};
+    CUresult r = encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box,
+                              CU_TENSOR_MAP_SWIZZLE_128B);
+    if (r != CUDA_SUCCESS) { set_last_error("tf_ext_attn: cuTensorMapEncodeTiled failed: %d", (int)r); return TF_ERR_DRIVER; }
+    return TF_OK;
+  };
+  if (int e = make(&map_q, q, q_tok_stride, q_samples_total, kBlockM)) return e;
+  if (int e = make(&map_k, k, kv_tok_stride, kv_samples_total, kBlockN)) return e;
+  if (int e = make(&map_v, v, kv_tok_stride, kv_samples_total, kBlockN)) return e;
+  AttnParams prm;
+  prm.S = S; prm.heads = heads; prm.d = d; prm.n_out = n_out;
+  prm.tiles_m = (S + 2 * kBlockM - 1) / (2 * kBlockM);
+  prm.handoff = 0;
+  prm.stages = stages;
+  prm.scale_log2 = scale * 1.4426950408889634f;
+  prm.out_tok_stride = (long long)heads * d;
+  auto kern = ext_attn_q4_kernel<kPoly16, kOnes>;
+  if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes),
+                 "tf_ext_attn smem attribute"))
+    return TF_ERR_CUDA;
+  const long long grid = (long long)n_out * heads * prm.tiles_m;
+  kern<<<(unsigned)grid, 640, smem_bytes, stream>>>(map_q, map_k, map_v, tab, prm, static_cast<__half*>(out));
   return check_cuda(cudaGetLastError(), "tf_ext_attn launch");
 }
 
@@ -731,15 +1182,46 @@ int launch_ext_attn(const void* q, const void* k, const void* v, long long q_tok
                     int q_samples_total, int kv_samples_total, const AttnTable& tab, int n_out, int S, int heads,
                     int d, float scale, void* out, cudaStream_t stream) {
   if (n_out == 0 || S == 0) return TF_OK;
-  // A/B switch for profiling: TF_EXT_ATTN_MODE = v1 (one query tile per CTA) | pp128 | pp64
+  // A/B switches for profiling: TF_EXT_ATTN_MODE=v1 forces the one-query-tile kernel; TF_EXT_ATTN_POLY=<k> evaluates k
+  // of every 16 exp2 on the FMA pipe; TF_EXT_ATTN_ONES=0/1 row sums in registers / by the tensor core.
   static const char* mode = getenv("TF_EXT_ATTN_MODE");
+  static const char* env_poly = getenv("TF_EXT_ATTN_POLY");
+  static const char* env_ones = getenv("TF_EXT_ATTN_ONES");
   const bool force_v1 = mode && mode[0] == 'v';
   if (d <= 64 && S > 128 && !force_v1) {
-    if (mode && mode[2] == '6')
-      return launch_pp<64>(q, k, v, q_tok_stride, kv_tok_stride, q_samples_total, kv_samples_total, tab, n_out, S,
-                           heads, d, scale, out, stream);
-    return launch_pp<128>(q, k, v, q_tok_stride, kv_tok_stride, q_samples_total, kv_samples_total, tab, n_out, S,
-                          heads, d, scale, out, stream);
+    const bool can_ones = (d % 16) != 0;            // a zero-padded column inside the P V MMA's N exists
+    const bool ones = can_ones && (env_ones ? atoi(env_ones) != 0 : kDefaultOnes);
+    const bool pp = mode && mode[0] == 'p';         // TF_EXT_ATTN_MODE=pp: the ping-pong kernel (one stream per query tile)
+    const int poly = env_poly ? atoi(env_poly) : (pp ? 0 : (ones ? kDefaultPolyOnes : kDefaultPoly));
+#define TF_PP(P, O)                                                                                              \
+    return launch_pp<128, P, O>(q, k, v, q_tok_stride, kv_tok_stride, q_samples_total, kv_samples_total, tab, n_out, \
+                                S, heads, d, scale, out, stream)
+#define TF_Q4(P, O)                                                                                              \
+    return launch_q4<P, O>(q, k, v, q_tok_stride, kv_tok_stride, q_samples_total, kv_samples_total, tab, n_out, S,  \
+                           heads, d, scale, out, stream)
+    if (pp) {
+      if (ones) { if (poly == 0) TF_PP(0, true); TF_PP(4, true); }
+      if (poly == 0) TF_PP(0, false);
+      TF_PP(4, false);
+    }
+    if (ones) {
+      switch (poly) {
+        case 0: TF_Q4(0, true);
+        case 2: TF_Q4(2, true);
+        case 3: TF_Q4(3, true);
+        case 4: TF_Q4(4, true);
+        case 5: TF_Q4(5, true);
+        default: TF_Q4(6, true);
+      }
+    }
+    switch (poly) {
+      case 0: TF_Q4(0, false);
+      case 2: TF_Q4(2, false);
+      case 3: TF_Q4(3, false);
+      default: TF_Q4(4, false);
+    }
+#undef TF_PP
+#undef TF_Q4
   }
   if (d <= 64)
     return launch_cfg<1, 128>(q, k, v, q_tok_stride, kv_tok_stride, q_samples_total, kv_samples_total, tab, n_out,

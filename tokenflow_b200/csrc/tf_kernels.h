@@ -22,8 +22,15 @@ int launch_unit_rows(const void* x, int x_is_f32, long long rows, int dim, long 
 int launch_layernorm_unit_rows(const void* x_f16, long long rows, int dim, long long row_stride, const float* gamma,
                                const float* beta, float eps, void* out_f16, cudaStream_t stream);
 
+int launch_layernorm_rows(const void* x_f16, long long rows, int dim, long long row_stride, const float* gamma,
+                          const float* beta, float eps, void* y_out, long long y_row_stride, void* unit_out,
+                          long long unit_row_stride, long long unit_rows, cudaStream_t stream);
+
+int launch_cfg_ddim(const void* eps_uncond, const void* eps_cond, const void* x, const float* coef_dev, float guidance,
+                    long long n, void* out, cudaStream_t stream);
+
 int launch_propagate(const void* A, const int32_t* idx_a, const int32_t* idx_b, const FrameTable& tab, int F,
-                     int S, int dim, int K, const void* residual, void* out, int out_is_f32,
+                     int S, int dim, int K, const void* residual, void* out, int out_is_f32, long long F_total,
                      cudaStream_t stream);
 
 int launch_nn_field(const void* x_unit, const void* piv_unit, const FrameTable& tab, int F, int S, int dim,

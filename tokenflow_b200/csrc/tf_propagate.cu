@@ -61,7 +61,8 @@ template <bool kOutF32, bool kResidual>
 __global__ void __launch_bounds__(kThreads)
 propagate_kernel(const __half* __restrict__ A, const int32_t* __restrict__ idx_a,
                  const int32_t* __restrict__ idx_b, FrameTable tab, int F, int S, int dim, int K,
-                 const __half* __restrict__ residual, void* __restrict__ out, int nvec, int rows_per_block) {
+                 const __half* __restrict__ residual, void* __restrict__ out, int nvec, int rows_per_block,
+                 long long stream_out) {      // stream_out: elements per stream in out / residual (= F_total*S*dim)
   const int f = blockIdx.y;
   const int r_in = threadIdx.x / nvec;
   const int vec = threadIdx.x - r_in * nvec;
@@ -70,7 +71,6 @@ propagate_kernel(const __half* __restrict__ A, const int32_t* __restrict__ idx_a
   const int kfb = tab.kf_b[f];
   const float w = tab.w[f];
   const float w2 = 1.0f - w;
-  const long long stream_out = (long long)F * S * dim;      // elements per stream in out / residual
   const long long kf_stride = (long long)S * dim;           // elements per keyframe slab
   const long long stream_A = (long long)K * kf_stride;
   const __half* A_a = A + (long long)kfa * kf_stride + vec * 8;
@@ -122,8 +122,10 @@ propagate_kernel(const __half* __restrict__ A, const int32_t* __restrict__ idx_a
 
 }  // namespace
 
+// `F` frames starting at the pointers given (a chunk of at most kMaxFrames frames of a call with `F_total`
+// frames: the three streams of out / residual are F_total*S*dim elements apart).
 int launch_propagate(const void* A, const int32_t* idx_a, const int32_t* idx_b, const FrameTable& tab, int F,
-                     int S, int dim, int K, const void* residual, void* out, int out_is_f32,
+                     int S, int dim, int K, const void* residual, void* out, int out_is_f32, long long F_total,
                      cudaStream_t stream) {
   if ((long long)F * S == 0) return TF_OK;
   const int nvec = dim >> 3;
@@ -142,7 +144,7 @@ int launch_propagate(const void* A, const int32_t* idx_a, const int32_t* idx_b, 
   const __half* Rh = static_cast<const __half*>(residual);
 #define TF_LAUNCH(OUTF32, RES)                                                                         \
   propagate_kernel<OUTF32, RES><<<grid, block, 0, stream>>>(Ah, idx_a, idx_b, tab, F, S, dim, K, Rh, out, nvec, \
-                                                            rows_per_block)
+                                                            rows_per_block, F_total * (long long)S * dim)
   if (out_is_f32) {
     if (residual) TF_LAUNCH(true, true); else TF_LAUNCH(true, false);
   } else {

@@ -102,15 +102,20 @@ int launch_unit_rows(const void* x, int x_is_f32, long long rows, int dim, long 
 }  // namespace tf
 
 // ------------------------------------------------------------------------------------------------
-// tf_layernorm_unit_rows — norm1 (LayerNorm) fused with the row L2-normalisation, for the frame pass.
+// tf_layernorm_rows / tf_layernorm_unit_rows — norm1 (LayerNorm) fused with what consumes it.
 //
-// In the frame pass the reference evaluates norm1 on all three streams (tokenflow_utils.py:323) but
-// only the source stream's output is ever used, and only as the NN-field query (:335): attn1 is
-// skipped.  This kernel therefore reads the source third of `hidden_states` (fp16) once and writes the
-// fp16 unit rows directly:   y = LN(x) in fp32 (autocast runs layer_norm in fp32: mean / biased
-// variance / eps inside the rsqrt / affine),  out = fp16(y / ||y||_2)  — the same arithmetic as
-// norm1 followed by tf_unit_rows, without materialising the fp32 [3B,S,dim] tensor or touching the
-// uncond/cond streams.  One warp per row, whole row held in registers (dim <= 1280).
+//   y    = LN(x) in fp32 (autocast runs layer_norm in fp32: mean / biased variance / eps inside the rsqrt /
+//          affine), rounded to fp16 — exactly the operand autocast hands to the to_q/to_k/to_v GEMMs
+//          (reference tokenflow_utils.py:323 -> :120-122);
+//   unit = fp16(y_fp32 / ||y_fp32||_2) — the row the NN field correlates (util.py:66-67 + the fp16 operand
+//          cast of util.py:68), from the UNROUNDED fp32 y like the reference's fp32 norm1 output.
+//
+// Frame pass: the reference evaluates norm1 on all three streams but only the source stream's output is ever
+// used, and only as the NN-field query (:335; attn1 is skipped) -> unit rows of the source third only, y is
+// never written.  Pivotal pass: y of every sample feeds the fused QKV projection, unit rows are wanted for the
+// source-stream samples (the first `unit_rows` rows) -> both outputs from ONE read of hidden_states, instead
+// of a 4-byte norm1 output that is re-read by three casts and one normalisation.
+// One warp per row, whole row held in registers (dim <= 1280).  Outputs may be strided (packed buffers).
 // ------------------------------------------------------------------------------------------------
 namespace tf {
 namespace {
@@ -118,15 +123,18 @@ namespace {
 constexpr int kLnMaxVecPerLane = 5;     // 5 x 8 halves x 32 lanes = 1280 channels
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-layernorm_unit_rows_kernel(const __half* __restrict__ x, long long rows, int dim, long long row_stride,
-                           const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                           __half* __restrict__ out) {
+layernorm_rows_kernel(const __half* __restrict__ x, long long rows, int dim, long long row_stride,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                      __half* __restrict__ y_out, long long y_row_stride, __half* __restrict__ unit_out,
+                      long long unit_row_stride, long long unit_rows) {
   const int lane = threadIdx.x & 31;
   const int nvec = dim >> 3;
   const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
   const float inv_dim = 1.0f / (float)dim;
   for (long long r = warp0; r < rows; r += nwarps) {
+    const bool want_unit = unit_out != nullptr && r < unit_rows;
+    if (y_out == nullptr && !want_unit) continue;
     const __half* xr = x + r * row_stride;
     float v[kLnMaxVecPerLane][8];
     float sum = 0.f;
@@ -179,13 +187,21 @@ layernorm_unit_rows_kernel(const __half* __restrict__ x, long long rows, int dim
           v[j][e] = y;
           ss += (double)y * y;
         }
+        if (y_out != nullptr) {
+          uint4 w;
+          __half2* h = reinterpret_cast<__half2*>(&w);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[j][2 * e], v[j][2 * e + 1]);
+          *reinterpret_cast<uint4*>(y_out + r * y_row_stride + vi * 8) = w;
+        }
       }
     }
+    if (!want_unit) continue;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     const float nrm = (float)sqrt(ss);
     const float rcp = __frcp_rn(nrm);
-    __half* orow = out + r * dim;
+    __half* orow = unit_out + r * unit_row_stride;
 #pragma unroll
     for (int j = 0; j < kLnMaxVecPerLane; ++j) {
       const int vi = lane + 32 * j;
@@ -203,19 +219,27 @@ layernorm_unit_rows_kernel(const __half* __restrict__ x, long long rows, int dim
 
 }  // namespace
 
-int launch_layernorm_unit_rows(const void* x_f16, long long rows, int dim, long long row_stride, const float* gamma,
-                               const float* beta, float eps, void* out_f16, cudaStream_t stream) {
-  if (rows == 0) return TF_OK;
+int launch_layernorm_rows(const void* x_f16, long long rows, int dim, long long row_stride, const float* gamma,
+                          const float* beta, float eps, void* y_out, long long y_row_stride, void* unit_out,
+                          long long unit_row_stride, long long unit_rows, cudaStream_t stream) {
+  if (rows == 0 || (y_out == nullptr && (unit_out == nullptr || unit_rows <= 0))) return TF_OK;
   if ((dim >> 3) > 32 * kLnMaxVecPerLane) {
-    set_last_error("tf_layernorm_unit_rows: dim=%d > %d is not supported", dim, 8 * 32 * kLnMaxVecPerLane);
+    set_last_error("tf_layernorm_rows: dim=%d > %d is not supported", dim, 8 * 32 * kLnMaxVecPerLane);
     return TF_ERR_UNSUPPORTED;
   }
-  long long blocks = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const long long work_rows = y_out != nullptr ? rows : (unit_rows < rows ? unit_rows : rows);
+  long long blocks = (work_rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const long long cap = (long long)sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  layernorm_unit_rows_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, stream>>>(
-      static_cast<const __half*>(x_f16), rows, dim, row_stride, gamma, beta, eps, static_cast<__half*>(out_f16));
-  return check_cuda(cudaGetLastError(), "tf_layernorm_unit_rows launch");
+  layernorm_rows_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, stream>>>(
+      static_cast<const __half*>(x_f16), work_rows, dim, row_stride, gamma, beta, eps, static_cast<__half*>(y_out),
+      y_row_stride, static_cast<__half*>(unit_out), unit_row_stride, unit_rows);
+  return check_cuda(cudaGetLastError(), "tf_layernorm_rows launch");
+}
+
+int launch_layernorm_unit_rows(const void* x_f16, long long rows, int dim, long long row_stride, const float* gamma,
+                               const float* beta, float eps, void* out_f16, cudaStream_t stream) {
+  return launch_layernorm_rows(x_f16, rows, dim, row_stride, gamma, beta, eps, nullptr, 0, out_f16, dim, rows, stream);
 }
 
 }  // namespace tf

@@ -52,6 +52,23 @@ class TokenFlowEditor(nn.Module):
         # a device tensor back (`int(t)` on a CUDA tensor is a full stream synchronisation)
         self._t_host = [int(t) for t in self.scheduler.timesteps]
         self._t_dev = {t: torch.tensor(t, device=self.device) for t in self._t_host}
+        self._t_index = {t: i for i, t in enumerate(self._t_host)}
+        # keyframe draws: world_size == 1 follows the reference (global CPU RNG, run_tokenflow_pnp.py:224); with
+        # several ranks every rank must draw the SAME keyframes, so the draws come from a dedicated generator
+        # seeded identically everywhere (config "keyframe_seed", default = the reference's seed 1) and are
+        # independent of whatever else consumes the global RNG on a rank.  config["check_keyframes"] additionally
+        # all-gathers the draw and asserts equality (debug / verify runs).
+        self._kf_gen = None
+        if world_size > 1 or "keyframe_seed" in self.config:
+            self._kf_gen = torch.Generator().manual_seed(int(self.config.get("keyframe_seed", self.config.get("seed", 1))))
+        self.comm = None                      # ops.Communicator (C-ABI NCCL all-gather), see attach_communicator
+        # DDIM coefficients per schedule position, on the device, for the fused CFG+DDIM kernel:
+        # sqrt(1-a_t), 1/sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev) as the fp32 values the eager expression uses
+        self._coef_table = self._make_coef_table()
+        self._graphs = {}                     # injection variant -> captured step
+        self._graph_pool = None
+        self._g_static = None
+        self._text_cache = {}
 
     # ------------------------------------------------------------------------------------
     def init_method(self):
@@ -98,7 +115,37 @@ class TokenFlowEditor(nn.Module):
     def draw_keyframes(self, n: int) -> torch.Tensor:
         """run_tokenflow_pnp.py:224 — one uniformly random frame inside every batch (CPU RNG)."""
         batch_size = self.config["batch_size"]
-        return torch.randint(batch_size, (n // batch_size,)) + torch.arange(0, n, batch_size)
+        if self._kf_gen is None:
+            r = torch.randint(batch_size, (n // batch_size,))
+        else:
+            r = torch.randint(batch_size, (n // batch_size,), generator=self._kf_gen)
+        idx = r + torch.arange(0, n, batch_size)
+        if self.world_size > 1 and self.config.get("check_keyframes", False):
+            import torch.distributed as dist
+            mine = idx.to(self.device if dist.get_backend(self.group) == "nccl" else "cpu")
+            everyone = [torch.empty_like(mine) for _ in range(self.world_size)]
+            dist.all_gather(everyone, mine, group=self.group)
+            for r_, other in enumerate(everyone):
+                if not torch.equal(other.cpu(), idx):
+                    raise RuntimeError(f"rank {self.rank} drew keyframes {idx.tolist()} but rank {r_} drew "
+                                       f"{other.cpu().tolist()}: the ranks' keyframe generators are out of step")
+        return idx
+
+    def _make_coef_table(self):
+        import numpy as np
+        sch, rows = self.scheduler, []
+        ratio = sch.num_train_timesteps // sch.num_inference_steps
+        for t in self._t_host:
+            a_t = float(sch._alpha(t))
+            a_prev = float(sch._alpha(t - ratio))
+            s1, s2 = np.float32((1 - a_t) ** 0.5), np.float32(a_t ** 0.5)
+            rows.append([float(s1), float(np.float32(1.0) / s2), float(np.float32(a_prev ** 0.5)),
+                         float(np.float32((1 - a_prev) ** 0.5))])
+        return torch.tensor(rows, dtype=torch.float32, device=self.device)
+
+    def attach_communicator(self, comm):
+        """Route the pivotal pass's all-gathers through the C ABI (tf_allgather) instead of torch.distributed."""
+        self.comm = comm
 
     def batched_denoise_step(self, x, t, indices):
         """run_tokenflow_pnp.py:220-233 (one process), or its frame-sharded form (world_size > 1).
@@ -204,14 +251,95 @@ class TokenFlowEditor(nn.Module):
             indices = torch.arange(len(x))
         return self.batched_denoise_step(x, self._t_host[i % len(self._t_host)], indices)
 
+    # ------------------------------------------------------------------------------------
+    # fused step: ONE UNet call per denoising step and rank, [pivotal samples | this rank's frames x 3 streams]
+    # ------------------------------------------------------------------------------------
+    def _pivotal_slots(self, K: int):
+        """(stream, keyframe) of every pivotal sample this rank runs, in batch order.  One rank: the reference's
+        [src | uncond | cond] x K batch.  Several ranks: this rank's m = ceil(3K/G) slots of that order (the tail is
+        padded with repeats of the last sample, whose results are ignored)."""
+        G, r = self.world_size, self.rank
+        if G == 1:
+            return [divmod(i, K) for i in range(3 * K)], None
+        shard = self.hooks.PivotalShard(G, r, K, self.group, comm=self.comm)
+        return [divmod(min(i, 3 * K - 1), K) for i in shard.slots], shard
+
+    def _fused_text(self, slots, per):
+        key = (tuple(slots), per)
+        text = self._text_cache.get(key)
+        if text is None:
+            emb = [self.pnp_guidance_embeds[0] if s_ == 0 else self.text_embeds[s_ - 1] for s_, _ in slots]
+            text = torch.cat([torch.stack(emb), self.pnp_guidance_embeds.repeat(per, 1, 1),
+                              torch.repeat_interleave(self.text_embeds, per, dim=0)])
+            self._text_cache = {key: text}
+        return text
+
+    def _fused_compute(self, x, src_all, piv_idx, t_dev, t_int, coef, slots, shard):
+        """Device work of one fused step.  Everything that varies from step to step arrives in device tensors
+        (`piv_idx`: which latents are the pivotal samples, `t_dev`, `coef`: the DDIM coefficients), so the same
+        function body can be captured once into a CUDA graph and replayed (run_tokenflow_pnp.py:195-233)."""
+        h, G, r = self.hooks, self.world_size, self.rank
+        N = x.shape[0]
+        per = N // G
+        lo = r * per
+        n_piv = len(slots)
+        piv_lat = torch.cat([src_all, x]).index_select(0, piv_idx)       # slot (s, f): src[kf_f] if s == 0 else x[kf_f]
+        xs, srcs = x[lo:lo + per], src_all[lo:lo + per]
+        latent_model_input = torch.cat([piv_lat, srcs, xs, xs])
+        text = self._fused_text(slots, per)
+        h.register_time(self, t_int)
+        h.register_pivotal(self, False)
+        h.register_shard(self, shard)
+        h.register_frame_table(self, *self.frame_table(list(range(lo, lo + per))))
+        h.register_fused(self, n_piv)
+        try:
+            noise_pred = self.unet(latent_model_input, t_dev, encoder_hidden_states=text)['sample'][n_piv:]
+        finally:
+            h.register_fused(self, 0)
+            h.register_shard(self, None)
+        _, npu, npc = noise_pred.chunk(3)
+        ops = self._cuda_ops()
+        if ops is not None and coef is not None and npu.dtype == torch.float16 and xs.dtype == torch.float16:
+            x_local = ops.cfg_ddim(npu, npc, xs, coef, self.config["guidance_scale"])     # one kernel, same roundings
+        else:
+            noise_pred = npu + self.config["guidance_scale"] * (npc - npu)
+            x_local = self.scheduler.step(noise_pred, t_int, xs)['prev_sample'].contiguous()
+        if G == 1:
+            return x_local
+        if self.comm is not None and x_local.is_cuda:
+            return self.comm.all_gather(x_local)
+        import torch.distributed as dist
+        out = torch.empty_like(x)
+        dist.all_gather_into_tensor(out, x_local, group=self.group)
+        return out
+
+    def _cuda_ops(self):
+        """The CUDA op object if the hooks run on it (None under the oracle test seam / on CPU)."""
+        if self.device.type != "cuda":
+            return None
+        ops = self.hooks._ops() if hasattr(self.hooks, "_ops") else None
+        return ops if hasattr(ops, "cfg_ddim") else None
+
+    def _piv_index_list(self, kf_list, slots, N):
+        return [kf_list[f_] if s_ == 0 else N + kf_list[f_] for s_, f_ in slots]
+
+    def _variant(self, t_int):
+        """Which hooks inject at this timestep — the only way `t` changes the captured kernel sequence."""
+        if self.config.get("mode", "pnp") != "pnp":
+            return (False, False)
+        qk = {int(v) for v in (self.qk_injection_timesteps.tolist() if torch.is_tensor(self.qk_injection_timesteps)
+                               else self.qk_injection_timesteps)}
+        conv = {int(v) for v in (self.conv_injection_timesteps.tolist() if torch.is_tensor(self.conv_injection_timesteps)
+                                 else self.conv_injection_timesteps)}
+        return (t_int in qk or t_int == 1000, t_int in conv or t_int == 1000)
+
     @torch.no_grad()
     def _fused_step(self, x, t, indices):
         """One UNet call per denoising step and rank: [pivotal samples | this rank's frames x 3 streams]."""
-        h, G, r = self.hooks, self.world_size, self.rank
         N, B = len(x), self.config["batch_size"]
         K = N // B
-        assert N % G == 0, "frames must divide evenly over the ranks"
-        t_int, t = self._timestep_pair(t)
+        assert N % self.world_size == 0, "frames must divide evenly over the ranks"
+        t_int, t_dev = self._timestep_pair(t)
         pivotal_idx = self.draw_keyframes(N)
         kf_list = pivotal_idx.tolist()
         self.keyframe_log.append(kf_list)
@@ -220,49 +348,88 @@ class TokenFlowEditor(nn.Module):
                 and torch.equal(indices, torch.arange(indices.numel()))):
             src_all = src_all[indices]                        # (identity in the drivers: all frames, in order)
         src_all = src_all.to(x.device, x.dtype)
-        h.register_time(self, t_int)
-        if G == 1:                                            # the reference's pivotal batch: [src | uncond | cond] x K
-            shard = None
-            x_kf = torch.stack([x[j] for j in kf_list])       # host-side index list: no index tensor upload
-            piv_lat = torch.cat([torch.stack([src_all[j] for j in kf_list]), x_kf, x_kf])
-            piv_emb = torch.cat([self.pnp_guidance_embeds.repeat(K, 1, 1),
-                                 torch.repeat_interleave(self.text_embeds, K, dim=0)])
-        else:                                                 # this rank's m of the 3K (stream, keyframe) samples
-            shard = h.PivotalShard(G, r, K, self.group)
-            lat, emb = [], []
-            for i in shard.slots:
-                i = min(i, 3 * K - 1)                         # padding slots recompute the last sample
-                s_, f_ = divmod(i, K)
-                frame = int(pivotal_idx[f_])
-                lat.append(src_all[frame] if s_ == 0 else x[frame])
-                emb.append(self.pnp_guidance_embeds[0] if s_ == 0 else self.text_embeds[s_ - 1])
-            piv_lat, piv_emb = torch.stack(lat), torch.stack(emb)
-        per = N // G
-        lo = r * per
-        frames = list(range(lo, lo + per))
-        xs, srcs = x[lo:lo + per], src_all[lo:lo + per]
-        n_piv = piv_lat.shape[0]
-        latent_model_input = torch.cat([piv_lat, srcs, xs, xs])
-        text = torch.cat([piv_emb, self.pnp_guidance_embeds.repeat(per, 1, 1),
-                          torch.repeat_interleave(self.text_embeds, per, dim=0)])
-        h.register_pivotal(self, False)
-        h.register_shard(self, shard)
-        h.register_frame_table(self, *self.frame_table(frames))
-        h.register_fused(self, n_piv)
+        slots, shard = self._pivotal_slots(K)
+        idx_host = torch.tensor(self._piv_index_list(kf_list, slots, N), dtype=torch.int64)
+        i = self._t_index.get(t_int)
+        coef = self._coef_table[i] if i is not None else None
+        if self.config.get("cuda_graph", False) and self.device.type == "cuda" and coef is not None:
+            return self._graph_replay(x, src_all, idx_host, t_int, i, slots, shard)
+        piv_idx = idx_host.to(x.device, non_blocking=True) if x.is_cuda else idx_host
+        return self._fused_compute(x, src_all, piv_idx, t_dev, t_int, coef, slots, shard)
+
+    # ------------------------------------------------------------------------------------
+    # CUDA graphs: the fused step's shape is static, so it is captured once per injection
+    # variant (PnP: q/k + conv injection, conv injection only, none) and replayed.  Per replay the host only
+    # refreshes five small static inputs: latents, source latents, the pivotal gather index, the timestep and
+    # the DDIM coefficients.  TMA descriptors, frame tables and attention tables are kernel parameters baked at
+    # capture; NCCL all-gathers are captured in-graph.
+    # ------------------------------------------------------------------------------------
+    def _graph_replay(self, x, src_all, idx_host, t_int, i, slots, shard):
+        variant = self._variant(t_int)
+        st = self._g_static
+        if st is None or st["x"].shape != x.shape or st["x"].dtype != x.dtype:
+            st = self._g_static = {
+                "x": torch.empty_like(x), "src": torch.empty_like(x),
+                "idx": torch.zeros(len(idx_host), dtype=torch.int64, device=x.device),
+                "t": torch.zeros((), dtype=torch.int64, device=x.device),
+                "coef": torch.zeros(4, dtype=torch.float32, device=x.device)}
+            self._graphs = {}
+        if x.data_ptr() != st["x"].data_ptr():
+            st["x"].copy_(x, non_blocking=True)
+        if src_all.data_ptr() != st["src"].data_ptr():
+            st["src"].copy_(src_all, non_blocking=True)
+        st["idx"].copy_(idx_host.pin_memory(), non_blocking=True)
+        st["t"].copy_(self._t_dev[t_int], non_blocking=True)
+        st["coef"].copy_(self._coef_table[i], non_blocking=True)
+        entry = self._graphs.get(variant)
+        if entry is None:
+            entry = self._graphs[variant] = self._capture(st, t_int, slots, shard)
+        entry["graph"].replay()
+        entry["replays"] += 1
+        return entry["out"].clone()
+
+    def _capture(self, st, t_int, slots, shard):
+        ops = self._cuda_ops()
+        run = lambda: self._fused_compute(st["x"], st["src"], st["idx"], st["t"], t_int, st["coef"], slots, shard)
+        # warm-up on a side stream (cuDNN autotuning, lazy initialisation, allocator growth) — not captured
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        saved_timing = ops._timing if ops is not None else None
+        if ops is not None:
+            ops._timing = None
+        with torch.cuda.stream(side):
+            for _ in range(int(self.config.get("graph_warmup", 2))):
+                run()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        events = [] if saved_timing is not None else None
+        if ops is not None:
+            ops._timing = events                # per-launch EXTERNAL events recorded as graph nodes
         try:
-            noise_pred = self.unet(latent_model_input, t, encoder_hidden_states=text)['sample'][n_piv:]
+            with torch.cuda.graph(graph, pool=self._graph_pool, capture_error_mode="thread_local"):
+                out = run()
         finally:
-            h.register_fused(self, 0)
-            h.register_shard(self, None)
-        _, npu, npc = noise_pred.chunk(3)
-        noise_pred = npu + self.config["guidance_scale"] * (npc - npu)
-        x_local = self.scheduler.step(noise_pred, t_int, xs)['prev_sample'].contiguous()
-        if G == 1:
-            return x_local
-        import torch.distributed as dist
-        out = torch.empty_like(x)
-        dist.all_gather_into_tensor(out, x_local, group=self.group)
-        return out
+            if ops is not None:
+                ops._timing = saved_timing
+        if self._graph_pool is None:
+            self._graph_pool = graph.pool()
+        return {"graph": graph, "out": out, "events": events, "replays": 0}
+
+    def graph_kernel_times(self):
+        """{kernel: {"launches", "ms", "work"}} of the LAST replay of every captured variant that has been
+        replayed (the event nodes are part of the graph; each replay overwrites their timestamps)."""
+        torch.cuda.synchronize()
+        agg = {}
+        for entry in self._graphs.values():
+            if not entry["replays"] or not entry["events"]:
+                continue
+            for name, work, s_, e_ in entry["events"]:
+                a = agg.setdefault(name, {"launches": 0, "ms": 0.0, "work": 0.0})
+                a["launches"] += 1
+                a["ms"] += s_.elapsed_time(e_)
+                a["work"] += work
+        return agg
 
     # ------------------------------------------------------------------------------------
     # host-buffer entry point (bench `e2e`): latents live in pinned host memory

@@ -19,6 +19,7 @@ import torch
 LIB_NAME = "libtokenflow_b200.so"
 TF_MAX_FRAMES = 64
 TF_MAX_ATTN_SAMPLES = 160
+TF_COMM_ID_BYTES = 128
 
 _c_i32p = ctypes.POINTER(ctypes.c_int32)
 _c_f32p = ctypes.POINTER(ctypes.c_float)
@@ -33,6 +34,16 @@ _SIGNATURES = {
     "tf_layernorm_unit_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int64,
                                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p,
                                               ctypes.c_void_p]),
+    "tf_layernorm_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p,
+                                         ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p, ctypes.c_int64,
+                                         ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
+    "tf_cfg_ddim": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float,
+                                   ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
+    "tf_comm_nccl_version": (ctypes.c_int, []),
+    "tf_comm_unique_id": (ctypes.c_int, [ctypes.c_void_p]),
+    "tf_comm_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    "tf_allgather": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
+    "tf_comm_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "tf_nn_field": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _c_i32p, _c_i32p, ctypes.c_int, ctypes.c_int,
                                    ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "tf_propagate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _c_i32p, _c_i32p, _c_f32p,
@@ -148,7 +159,9 @@ class CudaOps:
     def _timed(self, name: str, work: float, fn):
         if self._timing is None:
             return fn()
-        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ext = torch.cuda.is_current_stream_capturing()    # inside a CUDA-graph capture: event-record NODES
+        start = torch.cuda.Event(enable_timing=True, external=ext)
+        end = torch.cuda.Event(enable_timing=True, external=ext)
         start.record()
         out = fn()
         end.record()
@@ -185,25 +198,89 @@ class CudaOps:
                                   x2.stride(0), out.data_ptr(), self._stream()), "tf_unit_rows"))
         return out.view(*x.shape)
 
+    @staticmethod
+    def _affine_f32(norm: torch.nn.LayerNorm, device):
+        """fp32 copies of norm.weight / norm.bias for the fused LayerNorm kernels, re-made whenever either
+        parameter's storage or version counter changes (load_state_dict, .half(), in-place updates)."""
+        key = (norm.weight.data_ptr(), norm.weight._version, norm.bias.data_ptr(), norm.bias._version, str(device))
+        cache = norm.__dict__.get("_tf_affine_f32")
+        if cache is None or cache[0] != key:
+            cache = (key, norm.weight.detach().to(device=device, dtype=torch.float32).contiguous(),
+                     norm.bias.detach().to(device=device, dtype=torch.float32).contiguous())
+            norm.__dict__["_tf_affine_f32"] = cache
+        return cache[1], cache[2]
+
+    @staticmethod
+    def _ln_fusable(x: torch.Tensor, norm) -> bool:
+        return (x.dtype == torch.float16 and x.shape[-1] <= 1280 and getattr(norm, "weight", None) is not None
+                and getattr(norm, "bias", None) is not None and tuple(norm.normalized_shape) == (x.shape[-1],))
+
     def layernorm_unit_rows(self, x: torch.Tensor, norm: torch.nn.LayerNorm) -> torch.Tensor:
         """fp16 [..., dim] → fp16 unit rows of LayerNorm(x) (fp32 statistics): norm1 + unit_rows in one
         pass over the source stream (reference tokenflow_utils.py:323 + util.py:66-67)."""
         dim = x.shape[-1]
-        if x.dtype != torch.float16 or dim > 1280 or norm.weight is None or norm.bias is None:
+        if not self._ln_fusable(x, norm):
             return self.unit_rows(norm(x))                       # shapes the fused kernel does not cover
-        cache = norm.__dict__.get("_tf_affine_f32")
-        if cache is None or cache[0] is not norm.weight or cache[1].device != x.device:
-            cache = (norm.weight, norm.weight.detach().float().contiguous(), norm.bias.detach().float().contiguous())
-            norm.__dict__["_tf_affine_f32"] = cache
+        gamma, beta = self._affine_f32(norm, x.device)
         x2 = x.reshape(-1, dim)
         if x2.stride(-1) != 1 or x2.stride(0) % 8:
             x2 = x2.contiguous()
         out = torch.empty(x2.shape, dtype=torch.float16, device=x.device)
         self._timed("tf_layernorm_unit_rows", x2.shape[0] * dim * 4, lambda: self._check(
-            self.lib.tf_layernorm_unit_rows(x2.data_ptr(), x2.shape[0], dim, x2.stride(0), cache[1].data_ptr(),
-                                            cache[2].data_ptr(), float(norm.eps), out.data_ptr(), self._stream()),
+            self.lib.tf_layernorm_unit_rows(x2.data_ptr(), x2.shape[0], dim, x2.stride(0), gamma.data_ptr(),
+                                            beta.data_ptr(), float(norm.eps), out.data_ptr(), self._stream()),
             "tf_layernorm_unit_rows"))
         return out.view(*x.shape)
+
+    def layernorm_rows(self, x: torch.Tensor, norm: torch.nn.LayerNorm, n_unit: int,
+                       y_out: Optional[torch.Tensor] = None, unit_out: Optional[torch.Tensor] = None):
+        """Pivotal-pass norm1 fused with its two consumers: x [b, S, dim] fp16 → (y, unit) with
+        y = fp16(LN(x)) [b, S, dim] (the QKV GEMM operand) and unit = fp16 unit rows of LN(x) for the first
+        `n_unit` samples [n_unit, S, dim] (the pivot features of the NN field) — one read of x
+        (reference tokenflow_utils.py:323 -> :120-122, :326-327, util.py:66-67).  `y_out` / `unit_out` may be
+        views into packed buffers (last dim contiguous, row pitch a multiple of 8)."""
+        b, S, dim = x.shape
+        if not self._ln_fusable(x, norm):
+            y = norm(x)
+            unit = self.unit_rows(y[:n_unit]) if n_unit else None
+            if y_out is not None:
+                y_out.copy_(y); y = y_out
+            if unit_out is not None and unit is not None:
+                unit_out.copy_(unit); unit = unit_out
+            return y, unit
+        gamma, beta = self._affine_f32(norm, x.device)
+        x2 = x.reshape(-1, dim)
+        if x2.stride(-1) != 1 or x2.stride(0) % 8:
+            x2 = x2.contiguous()
+        y = torch.empty((b, S, dim), dtype=torch.float16, device=x.device) if y_out is None else y_out
+        unit = None
+        if n_unit:
+            unit = torch.empty((n_unit, S, dim), dtype=torch.float16, device=x.device) if unit_out is None else unit_out
+        def pitch(t):      # row pitch of a [.., S, dim] view whose rows are equally spaced
+            assert t.stride(-1) == 1 and t.stride(-2) % 8 == 0 and (t.shape[0] <= 1 or t.stride(0) == S * t.stride(-2))
+            return t.stride(-2)
+        self._timed("tf_layernorm_rows", x2.shape[0] * dim * 4 + n_unit * S * dim * 2, lambda: self._check(
+            self.lib.tf_layernorm_rows(x2.data_ptr(), x2.shape[0], dim, x2.stride(0), gamma.data_ptr(), beta.data_ptr(),
+                                       float(norm.eps), y.data_ptr(), pitch(y),
+                                       unit.data_ptr() if unit is not None else None,
+                                       pitch(unit) if unit is not None else dim, n_unit * S, self._stream()),
+            "tf_layernorm_rows"))
+        return y, unit
+
+    def cfg_ddim(self, eps_uncond: torch.Tensor, eps_cond: torch.Tensor, x: torch.Tensor, coef: torch.Tensor,
+                 guidance: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Classifier-free guidance + DDIM update (reference run_tokenflow_pnp.py:213-217) in one pass;
+        `coef` = device fp32 [4]: sqrt(1-a_t), 1/sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev)."""
+        assert eps_uncond.dtype == eps_cond.dtype == x.dtype == torch.float16 and coef.dtype == torch.float32
+        eu, ec, xx = (t if t.is_contiguous() else t.contiguous() for t in (eps_uncond, eps_cond, x))
+        assert eu.shape == ec.shape == xx.shape
+        if out is None:
+            out = torch.empty_like(xx)
+        n = xx.numel()
+        self._timed("tf_cfg_ddim", n * 8.0, lambda: self._check(
+            self.lib.tf_cfg_ddim(eu.data_ptr(), ec.data_ptr(), xx.data_ptr(), coef.data_ptr(), float(guidance), n,
+                                 out.data_ptr(), self._stream()), "tf_cfg_ddim"))
+        return out
 
     def nn_field(self, x_unit: torch.Tensor, piv_unit: torch.Tensor, kf_a: Sequence[int],
                  kf_b: Sequence[int]) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
@@ -217,13 +294,10 @@ class CudaOps:
         idx_a = torch.empty((F_, S), dtype=torch.int32, device=x_unit.device)
         any_b = any(int(b) >= 0 for b in kf_b)
         idx_b = torch.empty((F_, S), dtype=torch.int32, device=x_unit.device) if any_b else None
-        for f0 in range(0, F_, TF_MAX_FRAMES):
-            f1 = min(F_, f0 + TF_MAX_FRAMES)
-            pairs = (f1 - f0) + sum(1 for b in kf_b[f0:f1] if int(b) >= 0)
-            self._timed("tf_nn_field", 2.0 * pairs * S * S * dim, lambda: self._check(self.lib.tf_nn_field(
-                x_unit[f0:f1].data_ptr(), piv_unit.data_ptr(), _i32(kf_a[f0:f1]), _i32(kf_b[f0:f1]), f1 - f0, S, dim,
-                K, idx_a[f0:f1].data_ptr(), idx_b[f0:f1].data_ptr() if idx_b is not None else None,
-                self._stream()), "tf_nn_field"))
+        pairs = F_ + sum(1 for b in kf_b if int(b) >= 0)
+        self._timed("tf_nn_field", 2.0 * pairs * S * S * dim, lambda: self._check(self.lib.tf_nn_field(
+            x_unit.data_ptr(), piv_unit.data_ptr(), _i32(kf_a), _i32(kf_b), F_, S, dim, K, idx_a.data_ptr(),
+            idx_b.data_ptr() if idx_b is not None else None, self._stream()), "tf_nn_field"))
         return idx_a, idx_b
 
     def propagate(self, A: torch.Tensor, idx_a: torch.Tensor, idx_b: Optional[torch.Tensor],
@@ -241,24 +315,12 @@ class CudaOps:
             residual = residual.to(torch.float16).contiguous().view(3, F_, S, dim)
         out = torch.empty((3, F_, S, dim), dtype=out_dtype, device=A.device)
         assert out_dtype in (torch.float16, torch.float32)
-        if F_ <= TF_MAX_FRAMES:
-            self._timed("tf_propagate", propagate_bytes(F_, S, dim, kf_a, kf_b, residual is not None,
-                                                        out.element_size()), lambda: self._check(
-                self.lib.tf_propagate(
-                    A.data_ptr(), idx_a.data_ptr(), idx_b.data_ptr() if idx_b is not None else None, _i32(kf_a),
-                    _i32(kf_b), _f32(w), F_, S, dim, K, residual.data_ptr() if residual is not None else None,
-                    out.data_ptr(), int(out_dtype == torch.float32), self._stream()), "tf_propagate"))
-        else:  # the [3,F,S,dim] layout is not sliceable along F without strides: chunk through temporaries
-            for f0 in range(0, F_, TF_MAX_FRAMES):
-                f1 = min(F_, f0 + TF_MAX_FRAMES)
-                res_c = residual[:, f0:f1].contiguous() if residual is not None else None
-                out_c = torch.empty((3, f1 - f0, S, dim), dtype=out_dtype, device=A.device)
-                self._check(self.lib.tf_propagate(
-                    A.data_ptr(), idx_a[f0:f1].data_ptr(), idx_b[f0:f1].data_ptr() if idx_b is not None else None,
-                    _i32(kf_a[f0:f1]), _i32(kf_b[f0:f1]), _f32(w[f0:f1]), f1 - f0, S, dim, K,
-                    res_c.data_ptr() if res_c is not None else None, out_c.data_ptr(),
-                    int(out_dtype == torch.float32), self._stream()), "tf_propagate")
-                out[:, f0:f1] = out_c
+        self._timed("tf_propagate", propagate_bytes(F_, S, dim, kf_a, kf_b, residual is not None,
+                                                    out.element_size()), lambda: self._check(
+            self.lib.tf_propagate(
+                A.data_ptr(), idx_a.data_ptr(), idx_b.data_ptr() if idx_b is not None else None, _i32(kf_a),
+                _i32(kf_b), _f32(w), F_, S, dim, K, residual.data_ptr() if residual is not None else None,
+                out.data_ptr(), int(out_dtype == torch.float32), self._stream()), "tf_propagate"))
         return out.view(3 * F_, S, dim)
 
     def ext_attn(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: float,
@@ -298,3 +360,43 @@ class CudaOps:
             _i32([t[2] for t in table]), _i32([t[3] for t in table]), S, heads, d, float(scale), out.data_ptr(),
             self._stream()), "tf_ext_attn_fwd_table"))
         return out
+
+
+class Communicator:
+    """NCCL all-gather through the C ABI (tf_comm_init / tf_allgather, include/tokenflow_b200.h): the data
+    plane of the multi-GPU pivotal pass.  The 128-byte NCCL id travels over torch.distributed (control
+    plane), the collectives themselves are enqueued by the library on the current CUDA stream."""
+
+    def __init__(self, world_size: int, rank: int, group=None):
+        import torch.distributed as dist
+        self.lib = load_library()
+        self.world_size, self.rank = world_size, rank
+        idbuf = (ctypes.c_uint8 * TF_COMM_ID_BYTES)()
+        if rank == 0:
+            self._check(self.lib.tf_comm_unique_id(idbuf), "tf_comm_unique_id")
+        t = torch.tensor(list(idbuf), dtype=torch.uint8)
+        if dist.get_backend(group) == "nccl":
+            t = t.cuda()
+        dist.broadcast(t, src=0, group=group)
+        raw = bytes(t.cpu().tolist())
+        handle = ctypes.c_void_p()
+        self._check(self.lib.tf_comm_init(ctypes.create_string_buffer(raw, TF_COMM_ID_BYTES), world_size, rank,
+                                          ctypes.byref(handle)), "tf_comm_init")
+        self.handle = handle
+
+    def _check(self, status, what):
+        if status != 0:
+            raise TokenflowB200Error(f"{what} failed (status {status}): "
+                                     f"{self.lib.tf_last_error().decode(errors='replace')}")
+
+    def all_gather(self, t: torch.Tensor) -> torch.Tensor:
+        t = t.contiguous()
+        out = torch.empty((self.world_size * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        self._check(self.lib.tf_allgather(self.handle, t.data_ptr(), out.data_ptr(), t.numel() * t.element_size(),
+                                          torch.cuda.current_stream().cuda_stream), "tf_allgather")
+        return out
+
+    def destroy(self):
+        if self.handle:
+            self.lib.tf_comm_destroy(self.handle)
+            self.handle = None

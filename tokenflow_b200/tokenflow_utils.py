@@ -115,12 +115,17 @@ class PivotalShard:
     therefore reproduces the reference's [3K, S, dim] layout in its first 3K slabs.  Collectives go
     through torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU tests)."""
 
-    def __init__(self, world_size: int, rank: int, n_keyframes: int, group=None):
+    def __init__(self, world_size: int, rank: int, n_keyframes: int, group=None, comm=None):
         self.world_size, self.rank, self.K, self.group = world_size, rank, n_keyframes, group
+        self.comm = comm                      # ops.Communicator (tf_allgather through the C ABI) or None
         self.m = -(-3 * n_keyframes // world_size)
         self.slots = list(range(rank * self.m, (rank + 1) * self.m))     # global sample ids (>= 3K: padding)
+        self.n_collectives = 0
 
     def all_gather(self, t: torch.Tensor) -> torch.Tensor:
+        self.n_collectives += 1
+        if self.comm is not None and t.is_cuda:
+            return self.comm.all_gather(t)
         import torch.distributed as dist
         t = t.contiguous()
         out = torch.empty((self.world_size * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
@@ -144,14 +149,29 @@ class PivotalShard:
         return tab
 
 
+def _conv_injection_site(diffusion_model):
+    """`up_blocks[1].resnets[1]` (reference :21, :102) whether the caller passes the wrapper (`.unet`) or the
+    UNet itself.  A model whose conv-injection hook is installed but whose site cannot be found is an error:
+    the fused / sharded batch layouts would otherwise be injected as naive thirds, silently."""
+    unet = getattr(diffusion_model, "unet", diffusion_model)
+    try:
+        return unet.up_blocks[1].resnets[1]
+    except (AttributeError, IndexError, TypeError):
+        for _, m in diffusion_model.named_modules():
+            if getattr(m, "injection_schedule", None) is not None and isinstance_str(m, "ResnetBlock2D"):
+                raise RuntimeError("tokenflow_b200: a conv-injection hook is registered but up_blocks[1].resnets[1] "
+                                   "cannot be reached from the module passed to register_fused / register_shard")
+        return None
+
+
 def register_fused(diffusion_model, n_pivotal: int):
     """Fused pass: the next UNet call carries `n_pivotal` pivotal samples followed by the frame samples
     ([source | uncond | cond] thirds).  0 restores the reference's separate passes."""
     for module in _transformer_blocks(diffusion_model):
         module._tf_fused = int(n_pivotal)
-    unet = getattr(diffusion_model, "unet", None)
-    if unet is not None:
-        unet.up_blocks[1].resnets[1]._tf_fused = int(n_pivotal)
+    res = _conv_injection_site(diffusion_model)
+    if res is not None:
+        res._tf_fused = int(n_pivotal)
 
 
 def register_shard(diffusion_model, shard: Optional[PivotalShard]):
@@ -159,9 +179,9 @@ def register_shard(diffusion_model, shard: Optional[PivotalShard]):
     for module in _transformer_blocks(diffusion_model):
         module._tf_shard = shard
         module.attn1._tf_shard = shard
-    unet = getattr(diffusion_model, "unet", None)
-    if unet is not None:
-        unet.up_blocks[1].resnets[1]._tf_shard = shard       # PnP conv-feature injection site
+    res = _conv_injection_site(diffusion_model)
+    if res is not None:
+        res._tf_shard = shard                                # PnP conv-feature injection site
 
 
 _ATTN_SITES_CACHE: "weakref.WeakKeyDictionary[torch.nn.Module, list]" = weakref.WeakKeyDictionary()
@@ -291,16 +311,58 @@ def register_conv_injection(model, injection_schedule):
 _INJECTED_SITES = {1: (1, 2), 2: (0, 1, 2), 3: (0, 1, 2)}   # reference :208, :289
 
 
+def _fused_weight(attn, names, dtype):
+    """cat([attn.<name>.weight ...]) in `dtype`, cached on the module and re-made when any of the weights
+    changes storage or version (load_state_dict, .half(), in-place updates)."""
+    ws = [getattr(attn, n).weight for n in names]
+    key = tuple((w.data_ptr(), w._version) for w in ws) + (dtype,)
+    cache = attn.__dict__.setdefault("_tf_fused_w", {})
+    hit = cache.get(names)
+    if hit is None or hit[0] != key:
+        hit = (key, torch.cat([w.detach().to(dtype) for w in ws], dim=0).contiguous())
+        cache[names] = hit
+    return hit[1]
+
+
 def _sa_forward(attn, pnp: bool):
     to_out = attn.to_out[0] if type(attn.to_out) is torch.nn.modules.container.ModuleList else attn.to_out
 
+    def fast_path(x, encoder_hidden_states):
+        """fp16 activations on a GPU with fp16 GEMM operands (fp16 weights, or autocast casting them): the
+        three projections run as ONE cuBLAS GEMM on the concatenated weight and q/k/v are strided views of
+        its output — the kernel addresses them by token stride."""
+        if encoder_hidden_states is not None or not x.is_cuda or x.dtype != torch.float16:
+            return False
+        if any(getattr(attn, n).bias is not None for n in ("to_q", "to_k", "to_v")):
+            return False
+        return torch.is_autocast_enabled() or attn.to_q.weight.dtype == torch.float16
+
     def forward(x, encoder_hidden_states=None, attention_mask=None):
+        inject = pnp and _in_schedule(attn)
+        shard = getattr(attn, "_tf_shard", None)
+        dim = attn.to_q.weight.shape[0]
+        if fast_path(x, encoder_hidden_states):
+            if shard is None:
+                qkv = torch.nn.functional.linear(x, _fused_weight(attn, ("to_q", "to_k", "to_v"), torch.float16))
+                q, k, v = qkv[..., :dim], qkv[..., dim:2 * dim], qkv[..., 2 * dim:]
+                out = _ops().ext_attn(q, k, v, attn.heads, attn.scale, inject)
+            else:
+                # sharded pivotal pass: ONE all-gather of [k | v | pivot unit rows] along the sample axis
+                # (+ one of q only while PnP-injecting, when the source stream's q lives on another rank)
+                q = torch.nn.functional.linear(x, attn.to_q.weight.to(torch.float16))
+                kv = torch.nn.functional.linear(x, _fused_weight(attn, ("to_k", "to_v"), torch.float16))
+                unit = attn.__dict__.pop("_tf_unit_local", None)
+                packed = shard.all_gather(kv if unit is None else torch.cat([kv, unit], dim=-1))
+                if unit is not None:
+                    attn._tf_unit_gathered = packed[..., 2 * dim:]
+                k_all, v_all = packed[..., :dim], packed[..., dim:2 * dim]
+                q_src = shard.all_gather(q) if inject else q
+                out = _ops().ext_attn_table(q_src, k_all, v_all, shard.attention_table(inject), attn.heads, attn.scale)
+            return to_out(out)
         ctx = x if encoder_hidden_states is None else encoder_hidden_states
         q = attn.to_q(x)
         k = attn.to_k(ctx)
         v = attn.to_v(ctx)
-        inject = pnp and _in_schedule(attn)
-        shard = getattr(attn, "_tf_shard", None)
         if shard is None:
             out = _ops().ext_attn(q, k, v, attn.heads, attn.scale, inject)
         else:                                    # keyframe K/V (and, when injecting, Q) all-gathered over NVLink
@@ -391,20 +453,42 @@ def make_tokenflow_attention_block(block_class: Type[torch.nn.Module]) -> Type[t
             """Self-attention stage of the pivotal pass (reference :311-327, :352-360, :394-397)."""
             ops = _ops()
             batch_size, sequence_length, dim = hidden_states.shape
-            norm_hidden_states = self.norm1(hidden_states)
             shard = getattr(self, "_tf_shard", None)
+            fused_ln = (hidden_states.is_cuda and hidden_states.dtype == torch.float16
+                        and hasattr(ops, "layernorm_rows") and not self.only_cross_attention
+                        and (torch.is_autocast_enabled() or self.norm1.weight.dtype == torch.float16))
             if shard is not None:
                 # sharded pivotal pass: this rank holds m of the 3K (stream, keyframe) samples
-                unit_all = shard.all_gather(ops.unit_rows(norm_hidden_states))
-                self._tf_pivot_unit = unit_all[:shard.K]                                  # source stream
-                self.pivot_hidden_states = norm_hidden_states
-                self.attn_output = self.attn1(norm_hidden_states, **cross_attention_kwargs)
+                if fused_ln:
+                    # one read of hidden_states -> fp16 norm1 output (QKV operand) + its unit rows; the unit rows
+                    # ride in the attention's K/V all-gather (one collective instead of two)
+                    norm_hidden_states, unit = ops.layernorm_rows(hidden_states, self.norm1, batch_size)
+                    self.attn1._tf_unit_local = unit
+                    self.pivot_hidden_states = norm_hidden_states
+                    self.attn_output = self.attn1(norm_hidden_states, **cross_attention_kwargs)
+                    unit_all = self.attn1.__dict__.pop("_tf_unit_gathered", None)
+                    if unit_all is None:                      # the closure took its generic path
+                        unit_all = shard.all_gather(self.attn1.__dict__.pop("_tf_unit_local", unit))
+                    self._tf_pivot_unit = unit_all[:shard.K].contiguous()              # source stream
+                else:
+                    norm_hidden_states = self.norm1(hidden_states)
+                    unit_all = shard.all_gather(ops.unit_rows(norm_hidden_states))
+                    self._tf_pivot_unit = unit_all[:shard.K]                              # source stream
+                    self.pivot_hidden_states = norm_hidden_states
+                    self.attn_output = self.attn1(norm_hidden_states, **cross_attention_kwargs)
                 self.kf_attn_output = shard.all_gather(self.attn_output)[:3 * shard.K]
             else:
                 n_frames = batch_size // 3
+                if fused_ln:
+                    norm_hidden_states, unit = ops.layernorm_rows(hidden_states, self.norm1, n_frames)
+                    self._tf_pivot_unit = unit
+                else:
+                    norm_hidden_states = self.norm1(hidden_states)
+                    self._tf_pivot_unit = None
                 # cache keyframe features (:326-327) — plus their fp16 unit rows for the NN field
                 self.pivot_hidden_states = norm_hidden_states.view(3, n_frames, sequence_length, dim)
-                self._tf_pivot_unit = ops.unit_rows(self.pivot_hidden_states[0])
+                if self._tf_pivot_unit is None:
+                    self._tf_pivot_unit = ops.unit_rows(self.pivot_hidden_states[0])
                 self.attn_output = self.attn1(
                     norm_hidden_states,
                     encoder_hidden_states=encoder_hidden_states if self.only_cross_attention else None,
@@ -430,8 +514,11 @@ def make_tokenflow_attention_block(block_class: Type[torch.nn.Module]) -> Type[t
             idx_a, idx_b = ops.nn_field(x_unit, self._tf_pivot_unit, kf_a, kf_b)          # :335-343
             out_dtype = torch.float32 if (_strict_dtype() and idx_b is not None) else None
             self._tf_nn_idx = (idx_a, idx_b)
-            return ops.propagate(kf.view(3, n_kf, sequence_length, dim), idx_a, idx_b, kf_a, kf_b, w,
-                                 residual=hidden_states, out_dtype=out_dtype)             # :361-397
+            out = ops.propagate(kf.view(3, n_kf, sequence_length, dim), idx_a, idx_b, kf_a, kf_b, w,
+                                residual=hidden_states, out_dtype=out_dtype)              # :361-397
+            if not torch.is_autocast_enabled() and out.dtype != hidden_states.dtype and not _strict_dtype():
+                out = out.to(hidden_states.dtype)    # fp16 kernel output inside a non-autocast (fp32) model
+            return out
 
     return TokenFlowBlock
 
