@@ -112,6 +112,17 @@ int tf_ext_attn_fwd_table(const void* q, int q_slabs, int64_t q_tok_stride, cons
                           const int32_t* n_kv, int S, int heads, int d, float scale, void* out,
                           tf_stream_t stream);
 
+/* The same for a RANGE of query tokens: only queries [q_row0, q_row0 + q_nrows) of every sample are computed
+ * (against all keys), and `out` is [slabs, q_nrows, heads*d] with row = token - q_row0.  q_row0 must be a
+ * multiple of 128.  The multi-GPU pivotal pass splits the query rows of ALL samples evenly over the ranks this
+ * way (every rank holds all K/V after the all-gather), which balances the attention work exactly and keeps
+ * paired (q/k-injected) samples together. */
+int tf_ext_attn_fwd_rows(const void* q, int q_slabs, int64_t q_tok_stride, const void* k, const void* v,
+                         int kv_slabs, int64_t kv_tok_stride, int n_out, const int32_t* out_slab,
+                         const int32_t* q_slab, const int32_t* k_slab0, const int32_t* v_slab0,
+                         const int32_t* n_kv, int S, int heads, int d, float scale, int q_row0, int q_nrows,
+                         void* out, tf_stream_t stream);
+
 /* Classifier-free guidance + DDIM update (eta = 0) of one denoising step, one pass over the latents.
  * Replaces run_tokenflow_pnp.py:213-217 (`u + g*(c - u)`, `scheduler.step(...)['prev_sample']`), with the
  * fp16 rounding sequence of the eager expression (bit-identical results).

@@ -72,18 +72,23 @@ class OracleOps:
     def ext_attn(self, q, k, v, heads: int, scale: float, inject: bool) -> torch.Tensor:
         return O.extended_attention(q, k, v, heads, scale, inject)
 
-    def ext_attn_table(self, q, k, v, table, heads: int, scale: float) -> torch.Tensor:
+    def ext_attn_table(self, q, k, v, table, heads: int, scale: float, row0: int = 0, nrows=None) -> torch.Tensor:
         """Sharded-pass form: output sample j attends with q[qs] to the nkv consecutive slabs
         k[k0:k0+nkv], v[v0:v0+nkv] (frame-major), per head — the same per-head softmax(q k^T scale) v
         as reference :173-179."""
         _, S, dim = q.shape
         d = dim // heads
+        nrows = S if nrows is None else int(nrows)
+        r1 = min(S, row0 + nrows)                      # query tokens [row0, r1); rows past S stay zero
         outs = []
         for (qs, k0, v0, nkv) in table:
-            qq = q[qs].reshape(S, heads, d).permute(1, 0, 2)
+            qq = q[qs, row0:r1].reshape(max(0, r1 - row0), heads, d).permute(1, 0, 2)
             kk = k[k0:k0 + nkv].reshape(nkv * S, heads, d).permute(1, 0, 2)
             vv = v[v0:v0 + nkv].reshape(nkv * S, heads, d).permute(1, 0, 2)
             sim = torch.bmm(qq, kk.transpose(-1, -2)) * scale
             o = torch.bmm(sim.softmax(dim=-1), vv)
-            outs.append(o.permute(1, 0, 2).reshape(S, dim))
+            o = o.permute(1, 0, 2).reshape(max(0, r1 - row0), dim)
+            if o.shape[0] < nrows:
+                o = torch.cat([o, o.new_zeros(nrows - o.shape[0], dim)])
+            outs.append(o)
         return torch.stack(outs)

@@ -2,7 +2,6 @@
 the oracle ops == the single-process loop.  Covers the shard plan, the all-gather ordering, the
 per-frame keyframe/weight tables and the sharded attention table."""
 import os
-import socket
 
 import pytest
 import torch
@@ -12,12 +11,13 @@ import torch.multiprocessing as mp
 from tokenflow_b200 import tokenflow_utils as tfu
 
 
-def _free_port():
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    p = s.getsockname()[1]
-    s.close()
-    return p
+def _init_file(tmp_path_factory=None):
+    """file:// rendezvous: no port to race for (ADVICE r1)."""
+    import tempfile
+    fd, path = tempfile.mkstemp(prefix="tf_b200_rdzv_")
+    os.close(fd)
+    os.unlink(path)
+    return path
 
 
 def _edit(world, rank, mode, steps, fused=False):
@@ -37,14 +37,14 @@ def _edit(world, rank, mode, steps, fused=False):
     return ed.sample_loop(x), ed.keyframe_log
 
 
-def _worker(rank, world, port, mode, steps, q, fused=False):
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
+def _worker(rank, world, rdzv, mode, steps, q, fused=False):
     torch.set_num_threads(2)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dist.init_process_group("gloo", init_method=f"file://{rdzv}", rank=rank, world_size=world)
     try:
         out, kf = _edit(world, rank, mode, steps, fused)
-        q.put((rank, out, kf))
+        # plain Python data on the queue: a torch tensor would travel by file-descriptor passing, which needs
+        # the sender alive until the parent has rebuilt it (the worker exits right after the put)
+        q.put((rank, out.numpy().tolist(), kf))
     finally:
         dist.destroy_process_group()
 
@@ -55,8 +55,8 @@ def test_two_rank_edit_equals_single_process(mode, steps, fused):
     want, kf_want = _edit(1, 0, mode, steps)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, steps, q, fused)) for r in range(2)]
+    rdzv = _init_file()
+    procs = [ctx.Process(target=_worker, args=(r, 2, rdzv, mode, steps, q, fused)) for r in range(2)]
     for p in procs:
         p.start()
     results = [q.get(timeout=300) for _ in procs]
@@ -65,7 +65,7 @@ def test_two_rank_edit_equals_single_process(mode, steps, fused):
         assert p.exitcode == 0
     for rank, out, kf in results:
         assert kf == kf_want
-        assert torch.allclose(out, want, atol=2e-4, rtol=1e-4), f"rank {rank}"
+        assert torch.allclose(torch.tensor(out), want, atol=2e-4, rtol=1e-4), f"rank {rank}"
 
 
 def test_shard_plan_and_attention_table():

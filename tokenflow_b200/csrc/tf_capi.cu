@@ -247,11 +247,15 @@ int tf_propagate(const void* A, const int32_t* idx_a, const int32_t* idx_b, cons
   return TF_OK;
 }
 
-int tf_ext_attn_fwd_table(const void* q, int q_slabs, int64_t q_tok_stride, const void* k, const void* v,
-                          int kv_slabs, int64_t kv_tok_stride, int n_out, const int32_t* out_slab,
-                          const int32_t* q_slab, const int32_t* k_slab0, const int32_t* v_slab0,
-                          const int32_t* n_kv, int S, int heads, int d, float scale, void* out,
-                          tf_stream_t stream) {
+int tf_ext_attn_fwd_rows(const void* q, int q_slabs, int64_t q_tok_stride, const void* k, const void* v,
+                         int kv_slabs, int64_t kv_tok_stride, int n_out, const int32_t* out_slab,
+                         const int32_t* q_slab, const int32_t* k_slab0, const int32_t* v_slab0,
+                         const int32_t* n_kv, int S, int heads, int d, float scale, int q_row0, int q_nrows,
+                         void* out, tf_stream_t stream) {
+  if (q_row0 < 0 || q_nrows < 0 || (q_row0 & 127)) {
+    set_last_error("tf_ext_attn: bad query row range [%d, +%d) (start must be a multiple of 128)", q_row0, q_nrows);
+    return TF_ERR_INVALID_ARGUMENT;
+  }
   if (n_out < 0 || S < 0 || heads <= 0 || d <= 0 || (d & 7) ||
       q_tok_stride < (int64_t)heads * d || kv_tok_stride < (int64_t)heads * d || (q_tok_stride & 7) ||
       (kv_tok_stride & 7)) {
@@ -259,7 +263,7 @@ int tf_ext_attn_fwd_table(const void* q, int q_slabs, int64_t q_tok_stride, cons
                    (long long)q_tok_stride, (long long)kv_tok_stride);
     return TF_ERR_INVALID_ARGUMENT;
   }
-  if (n_out == 0 || S == 0) return TF_OK;
+  if (n_out == 0 || S == 0 || q_nrows == 0 || q_row0 >= S) return TF_OK;
   if (!q || !k || !v || !out || !out_slab || !q_slab || !k_slab0 || !v_slab0 || !n_kv || !aligned16(q) ||
       !aligned16(k) || !aligned16(v) || !aligned16(out)) {
     set_last_error("tf_ext_attn: NULL or misaligned pointer");
@@ -273,13 +277,59 @@ int tf_ext_attn_fwd_table(const void* q, int q_slabs, int64_t q_tok_stride, cons
       return TF_ERR_INVALID_ARGUMENT;
     }
   }
+  // Samples that share q and k (PnP q/k injection: the uncond and cond sample of a keyframe, reference :124-130) have
+  // identical scores and probabilities: pair them and let one kernel compute S / P once and P [V_a | V_b] together.
+  std::vector<int> partner(n_out, -1);
+  int n_pairs = 0;
+  const int rows_here = (q_row0 + q_nrows < S ? q_row0 + q_nrows : S) - q_row0;
+  if (ext_attn_pairs_supported(rows_here, d)) {
+    for (int i = 0; i < n_out; ++i) {
+      if (partner[i] >= 0) continue;
+      for (int j = i + 1; j < n_out; ++j) {
+        if (partner[j] < 0 && q_slab[j] == q_slab[i] && k_slab0[j] == k_slab0[i] && n_kv[j] == n_kv[i] &&
+            v_slab0[j] != v_slab0[i] && out_slab[j] != out_slab[i]) {
+          partner[i] = j;
+          partner[j] = i;
+          ++n_pairs;
+          break;
+        }
+      }
+    }
+  }
+  if (n_pairs > 0) {
+    std::vector<int> lead;
+    for (int i = 0; i < n_out; ++i)
+      if (partner[i] > i) lead.push_back(i);
+    std::stable_sort(lead.begin(), lead.end(), [&](int a, int b) { return n_kv[a] > n_kv[b]; });
+    for (int p0 = 0; p0 < n_pairs; p0 += kMaxAttnPairs) {
+      const int nc = n_pairs - p0 < kMaxAttnPairs ? n_pairs - p0 : kMaxAttnPairs;
+      AttnPairTable ptab;
+      memset(&ptab, 0, sizeof(ptab));
+      for (int slot = 0; slot < nc; ++slot) {
+        const int i = lead[p0 + slot], j = partner[i];
+        ptab.p[slot].out_u = out_slab[i];
+        ptab.p[slot].out_c = out_slab[j];
+        ptab.p[slot].q_sample = q_slab[i];
+        ptab.p[slot].k_sample0 = k_slab0[i];
+        ptab.p[slot].v_u0 = v_slab0[i];
+        ptab.p[slot].v_c0 = v_slab0[j];
+        ptab.p[slot].n_kv = n_kv[i];
+      }
+      int e = launch_ext_attn_pairs(q, k, v, q_tok_stride, kv_tok_stride, q_slabs, kv_slabs, ptab, nc, S, heads, d, scale,
+                                    out, q_row0, q_nrows, static_cast<cudaStream_t>(stream));
+      if (e) return e;
+      g_launches += 1;
+    }
+  }
   // heavy samples (most key slabs) first: the hardware block scheduler then fills the tail of the
   // grid with the cheap own-frame (source stream) samples
-  std::vector<int> order(n_out);
-  for (int i = 0; i < n_out; ++i) order[i] = i;
+  std::vector<int> order;
+  for (int i = 0; i < n_out; ++i)
+    if (partner[i] < 0) order.push_back(i);
+  const int n_single = (int)order.size();
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return n_kv[a] > n_kv[b]; });
-  for (int s0 = 0; s0 < n_out; s0 += kMaxAttnSamples) {       // any number of samples: kMaxAttnSamples per launch
-    const int nc = n_out - s0 < kMaxAttnSamples ? n_out - s0 : kMaxAttnSamples;
+  for (int s0 = 0; s0 < n_single; s0 += kMaxAttnSamples) {    // any number of samples: kMaxAttnSamples per launch
+    const int nc = n_single - s0 < kMaxAttnSamples ? n_single - s0 : kMaxAttnSamples;
     AttnTable tab;
     memset(&tab, 0, sizeof(tab));
     for (int slot = 0; slot < nc; ++slot) {
@@ -291,11 +341,20 @@ int tf_ext_attn_fwd_table(const void* q, int q_slabs, int64_t q_tok_stride, cons
       tab.s[slot].n_kv = n_kv[i];
     }
     int e = launch_ext_attn(q, k, v, q_tok_stride, kv_tok_stride, q_slabs, kv_slabs, tab, nc, S, heads, d, scale, out,
-                            static_cast<cudaStream_t>(stream));
+                            q_row0, q_nrows, static_cast<cudaStream_t>(stream));
     if (e) return e;
     g_launches += 1;
   }
   return TF_OK;
+}
+
+int tf_ext_attn_fwd_table(const void* q, int q_slabs, int64_t q_tok_stride, const void* k, const void* v,
+                          int kv_slabs, int64_t kv_tok_stride, int n_out, const int32_t* out_slab,
+                          const int32_t* q_slab, const int32_t* k_slab0, const int32_t* v_slab0,
+                          const int32_t* n_kv, int S, int heads, int d, float scale, void* out,
+                          tf_stream_t stream) {
+  return tf_ext_attn_fwd_rows(q, q_slabs, q_tok_stride, k, v, kv_slabs, kv_tok_stride, n_out, out_slab, q_slab, k_slab0,
+                              v_slab0, n_kv, S, heads, d, scale, 0, S, out, stream);
 }
 
 int tf_ext_attn_fwd(const void* q, const void* k, const void* v, int64_t tok_stride, int n_frames, int S,

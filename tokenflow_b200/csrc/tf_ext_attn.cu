@@ -70,6 +70,9 @@ struct AttnParams {
   int handoff;            // ping-pong kernel: chunk index after which the MUFU token is handed over
   float scale_log2;       // scale * log2(e)
   long long out_tok_stride;   // elements between consecutive tokens of `out` (= heads*d)
+  int q_row0;             // first query token this launch computes (multi-GPU: query rows are split across ranks)
+  int q_row_end;          // one past the last query token (<= S)
+  int out_rows;           // rows per slab of `out`: out is [slabs, out_rows, heads*d], row = token - q_row0
 };
 
 template <int kDChunks, int kBlockN>
@@ -99,7 +102,7 @@ ext_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   const int sample_slot = blockIdx.x / per_sample;
   const int rem = blockIdx.x - sample_slot * per_sample;
   const int head = rem / prm.tiles_m;
-  const int m0 = (rem - head * prm.tiles_m) * kBlockM;
+  const int m0 = prm.q_row0 + (rem - head * prm.tiles_m) * kBlockM;
   const AttnSample smp = tab.s[sample_slot];
   const int out_sample = smp.out_sample;
   const int q_slab = smp.q_sample;
@@ -293,12 +296,12 @@ ext_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     tc_fence_after_sync();
     const float inv_l = 1.0f / l_run;
     const int p_tok = m0 + row;
-    __half* orow = out + ((long long)out_sample * S + p_tok) * prm.out_tok_stride + (long long)head * d;
+    __half* orow = out + ((long long)out_sample * prm.out_rows + (p_tok - prm.q_row0)) * prm.out_tok_stride + (long long)head * d;
     for (int c0 = 0; c0 < n_pv; c0 += 16) {
       uint32_t o[16];
       tmem_ld16(tmem_base + t_lane + kOCol + c0, o);
       tmem_wait_ld();
-      if (p_tok < S) {
+      if (p_tok < prm.q_row_end) {
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           if (c0 + g * 8 < d) {                     // d is a multiple of 8: whole 16-byte groups
@@ -346,7 +349,7 @@ ext_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 // ================================================================================================
 constexpr int kPPStagesMax = 12;
 constexpr bool kDefaultOnes = true;        // measured choices (profiles/r02_ext_attn_variants.md)
-constexpr int kDefaultPolyOnes = 0, kDefaultPoly = 0;
+constexpr int kDefaultPolyOnes = 3, kDefaultPoly = 4, kDefaultPolyPair = 3;
 struct AttnCtl2 {
   uint64_t q_full;
   uint64_t kv_full[kPPStagesMax];
@@ -406,7 +409,7 @@ ext_attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   const int sample_slot = blockIdx.x / per_sample;
   const int rem = blockIdx.x - sample_slot * per_sample;
   const int head = rem / prm.tiles_m;
-  const int m0 = (rem - head * prm.tiles_m) * (2 * kBlockM);
+  const int m0 = prm.q_row0 + (rem - head * prm.tiles_m) * (2 * kBlockM);
   const AttnSample smp = tab.s[sample_slot];
   const int tiles_per_slab = (S + kBlockN - 1) / kBlockN;
   const int T = smp.n_kv * tiles_per_slab;
@@ -677,12 +680,12 @@ ext_attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     }
     const float inv_l = 1.0f / l_run;
     const int p_tok = m0 + X * kBlockM + row;
-    __half* orow = out + ((long long)smp.out_sample * S + p_tok) * prm.out_tok_stride + (long long)head * d;
+    __half* orow = out + ((long long)smp.out_sample * prm.out_rows + (p_tok - prm.q_row0)) * prm.out_tok_stride + (long long)head * d;
     for (int c0 = 0; c0 < n_pv; c0 += 16) {
       uint32_t o[16];
       tmem_ld16(o_addr + c0, o);
       tmem_wait_ld();
-      if (p_tok < S) {
+      if (p_tok < prm.q_row_end) {
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           if (c0 + g * 8 < d) {
@@ -709,7 +712,7 @@ ext_attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 template <int kBlockN, int kPoly16, bool kOnes>
 int launch_pp(const void* q, const void* k, const void* v, long long q_tok_stride, long long kv_tok_stride,
               int q_samples_total, int kv_samples_total, const AttnTable& tab, int n_out, int S, int heads, int d,
-              float scale, void* out, cudaStream_t stream) {
+              float scale, void* out, int q_row0, int q_nrows, cudaStream_t stream) {
   constexpr int kQBytes = 2 * kBlockM * 128, kOnesBytes = 0, kStageBytes = 2 * kBlockN * 128;
   int stages = (227 * 1024 - 2048 - kQBytes - kOnesBytes) / kStageBytes;
   if (stages > kPPStagesMax) stages = kPPStagesMax;
@@ -729,7 +732,8 @@ int launch_pp(const void* q, const void* k, const void* v, long long q_tok_strid
   if (int e = make(&map_v, v, kv_tok_stride, kv_samples_total, kBlockN)) return e;
   AttnParams prm;
   prm.S = S; prm.heads = heads; prm.d = d; prm.n_out = n_out;
-  prm.tiles_m = (S + 2 * kBlockM - 1) / (2 * kBlockM);
+  prm.q_row0 = q_row0; prm.q_row_end = (q_row0 + q_nrows < S) ? q_row0 + q_nrows : S; prm.out_rows = q_nrows;
+  prm.tiles_m = (prm.q_row_end - q_row0 + 2 * kBlockM - 1) / (2 * kBlockM);
   static const char* env_handoff = getenv("TF_EXT_ATTN_HANDOFF");     // tuning knob (profiling)
   prm.handoff = env_handoff ? atoi(env_handoff) : (kBlockN / 32 - 2);
   prm.stages = stages;
@@ -809,7 +813,7 @@ ext_attn_q4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   const int sample_slot = blockIdx.x / per_sample;
   const int rem = blockIdx.x - sample_slot * per_sample;
   const int head = rem / prm.tiles_m;
-  const int m0 = (rem - head * prm.tiles_m) * (2 * kBlockM);
+  const int m0 = prm.q_row0 + (rem - head * prm.tiles_m) * (2 * kBlockM);
   const AttnSample smp = tab.s[sample_slot];
   const int tiles_per_slab = (S + kBlockN - 1) / kBlockN;
   const int T = smp.n_kv * tiles_per_slab;
@@ -1062,13 +1066,13 @@ ext_attn_q4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       const float inv_l = 1.0f / (a_l * l_run + a_r * mr.y);
       const float w_l = a_l * inv_l, w_r = a_r * inv_l;
       const int p_tok = m0 + X * kBlockM + row;
-      __half* orow = out + ((long long)smp.out_sample * S + p_tok) * prm.out_tok_stride + (long long)head * d;
+      __half* orow = out + ((long long)smp.out_sample * prm.out_rows + (p_tok - prm.q_row0)) * prm.out_tok_stride + (long long)head * d;
       for (int c0 = 0; c0 < n_pv; c0 += 16) {
         uint32_t ol[16], orr[16];
         tmem_ld16(o_addr + c0, ol);
         tmem_ld16(o_addr + 64 + c0, orr);
         tmem_wait_ld();
-        if (p_tok < S) {
+        if (p_tok < prm.q_row_end) {
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             if (c0 + g * 8 < d) {
@@ -1100,7 +1104,7 @@ ext_attn_q4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 template <int kPoly16, bool kOnes>
 int launch_q4(const void* q, const void* k, const void* v, long long q_tok_stride, long long kv_tok_stride,
               int q_samples_total, int kv_samples_total, const AttnTable& tab, int n_out, int S, int heads, int d,
-              float scale, void* out, cudaStream_t stream) {
+              float scale, void* out, int q_row0, int q_nrows, cudaStream_t stream) {
   constexpr int kBlockN = 128;
   constexpr int kQBytes = 2 * kBlockM * 128, kStageBytes = 2 * kBlockN * 128;
   int stages = (227 * 1024 - 1024 - (int)sizeof(AttnCtl4) - 64 - kQBytes) / kStageBytes;
@@ -1121,7 +1125,8 @@ int launch_q4(const void* q, const void* k, const void* v, long long q_tok_strid
   if (int e = make(&map_v, v, kv_tok_stride, kv_samples_total, kBlockN)) return e;
   AttnParams prm;
   prm.S = S; prm.heads = heads; prm.d = d; prm.n_out = n_out;
-  prm.tiles_m = (S + 2 * kBlockM - 1) / (2 * kBlockM);
+  prm.q_row0 = q_row0; prm.q_row_end = (q_row0 + q_nrows < S) ? q_row0 + q_nrows : S; prm.out_rows = q_nrows;
+  prm.tiles_m = (prm.q_row_end - q_row0 + 2 * kBlockM - 1) / (2 * kBlockM);
   prm.handoff = 0;
   prm.stages = stages;
   prm.scale_log2 = scale * 1.4426950408889634f;
@@ -1135,10 +1140,710 @@ int launch_q4(const void* q, const void* k, const void* v, long long q_tok_strid
   return check_cuda(cudaGetLastError(), "tf_ext_attn launch");
 }
 
+// ================================================================================================
+// Quad-stream kernel, shared accumulators ("q4s", head dim <= 64) — the default.
+//
+// Same 16 softmax warps as above (two query tiles x two key halves), but:
+//   * the fp16 probabilities get their OWN tensor-memory region instead of overwriting the scores, so the
+//     next score tile S_X[t+1] = Q_X K_{t+1}^T is issued as soon as the softmax warps have pulled S_X[t] into
+//     registers (barrier s_free) — not after P_X[t] V_t.  The score round trip (P V -> Q K^T -> commit ->
+//     wake-up, ~500 cycles during which the 8 warps of a query tile sat idle in the kernel above) disappears:
+//     every softmax warp streams tile after tile and the exp2 phase of all four warps of a sub-partition overlap;
+//   * the two key halves of a row share one accumulator O_X and therefore one running max: the two threads of
+//     a row (same lane, two warps on the same SM sub-partition) exchange their half-row maxima through shared
+//     memory and a 64-thread named barrier once per tile (~40 cycles against a ~1000-cycle phase); the lazy
+//     rescale decision is then identical in both warps and each rescales alternate 16-column chunks of O_X.
+// TMEM (512 columns): S_A [0,128)  S_B [128,256)  P_A [256,320)  P_B [320,384)  O_A [384,448)  O_B [448,512).
+// ================================================================================================
+struct AttnCtl4s {
+  uint64_t q_full;
+  uint64_t kv_full[kPPStagesMax];
+  uint64_t kv_empty[kPPStagesMax];
+  uint64_t v_ready[kPPStagesMax];
+  uint64_t s_full[2];          // [tile X]  Q K^T committed
+  uint64_t s_free[2];          // [tile X]  all 8 softmax warps hold S_X[t] in registers
+  uint64_t p_full[2];          // [tile X]  all 8 softmax warps stored their part of P_X[t]
+  uint64_t pv_done[2][2];      // [tile X][t & 1]
+  float xch[2][2][2][128];     // [t & 1][tile X][half][row]: half-row maxima (and, at the end, row sums)
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int kPoly16, bool kOnes>
+__global__ void __launch_bounds__(640, 1)
+ext_attn_q4s_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                    const __grid_constant__ CUtensorMap map_v, const AttnTable tab, const AttnParams prm,
+                    __half* __restrict__ out) {
+  constexpr int kBlockN = 128;
+  constexpr int kQTileBytes = kBlockM * 128;
+  constexpr int kQBytes = 2 * kQTileBytes;
+  constexpr int kTileBytes = kBlockN * 128;
+  constexpr int kStageBytes = 2 * kTileBytes;
+  constexpr int kPCol = 256, kOCol = 384;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_smem = smem;
+  uint8_t* ring = smem + kQBytes;
+  AttnCtl4s* ctl = reinterpret_cast<AttnCtl4s*>(ring + prm.stages * kStageBytes);
+
+  const int S = prm.S, d = prm.d, stages = prm.stages;
+  const int per_sample = prm.heads * prm.tiles_m;
+  const int sample_slot = blockIdx.x / per_sample;
+  const int rem = blockIdx.x - sample_slot * per_sample;
+  const int head = rem / prm.tiles_m;
+  const int m0 = prm.q_row0 + (rem - head * prm.tiles_m) * (2 * kBlockM);
+  const AttnSample smp = tab.s[sample_slot];
+  const int tiles_per_slab = (S + kBlockN - 1) / kBlockN;
+  const int T = smp.n_kv * tiles_per_slab;
+  const int ksteps = (d + 15) / 16;
+  const int n_pv = ((d + 15) / 16) * 16;
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_v);
+    mbar_init(&ctl->q_full, 1);
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&ctl->kv_full[i], 1);
+      mbar_init(&ctl->kv_empty[i], 2);
+      mbar_init(&ctl->v_ready[i], 1);
+    }
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(&ctl->s_full[x], 1);
+      mbar_init(&ctl->s_free[x], 8);
+      mbar_init(&ctl->p_full[x], 8);
+      mbar_init(&ctl->pv_done[x][0], 1);
+      mbar_init(&ctl->pv_done[x][1], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&ctl->tmem_base, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
+
+  if (warp < 4) {
+    warpgroup_reg_dec<64>();
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&ctl->q_full, (uint32_t)kQBytes);
+        tma_load_4d(q_smem, &map_q, &ctl->q_full, 0, head, m0, smp.q_sample);
+        tma_load_4d(q_smem + kQTileBytes, &map_q, &ctl->q_full, 0, head, m0 + kBlockM, smp.q_sample);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = 0; t < T; ++t) {
+          const int slab = t / tiles_per_slab;
+          const int n0 = (t - slab * tiles_per_slab) * kBlockN;
+          mbar_wait(&ctl->kv_empty[stage], phase ^ 1);
+          uint8_t* st = ring + stage * kStageBytes;
+          mbar_arrive_expect_tx(&ctl->kv_full[stage], (uint32_t)kStageBytes);
+          tma_load_4d(st, &map_k, &ctl->kv_full[stage], 0, head, n0, smp.k_sample0 + slab);
+          tma_load_4d(st + kTileBytes, &map_v, &ctl->kv_full[stage], 0, head, n0, smp.v_sample0 + slab);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1 || warp == 2) {
+      // ===================== MMA issuers: one warp per query tile (warp 1 -> A, warp 2 -> B) ==============
+      const int X = warp - 1;
+      const uint32_t idesc_qk = umma_idesc_f16(128, kBlockN, 0);
+      const uint32_t idesc_pv = umma_idesc_f16(128, (uint32_t)n_pv, 1);
+      constexpr uint32_t hi_kmaj = umma_desc_hi(1024);
+      const uint32_t q_lo = umma_desc_lo(smem_u32(q_smem + X * kQTileBytes), 16);
+      const uint32_t ring_k_lo = umma_desc_lo(smem_u32(ring), 16);
+      const uint32_t ring_v_lo = umma_desc_lo(smem_u32(ring + kTileBytes), kTileBytes);
+      constexpr uint32_t kStageStep = kStageBytes >> 4;
+      const uint32_t s_tmem = tmem_base + (uint32_t)(X * kBlockN);
+      const uint32_t p_tmem = tmem_base + kPCol + (uint32_t)(X * 64);
+      const uint32_t o_tmem = tmem_base + kOCol + (uint32_t)(X * 64);
+      auto issue_qk = [&](int st) {
+        const uint32_t k_lo = ring_k_lo + (uint32_t)st * kStageStep;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          if (ks < ksteps) tc_mma_ss_lh(s_tmem, q_lo + ks * 2, hi_kmaj, k_lo + ks * 2, hi_kmaj, idesc_qk, ks > 0 ? 1u : 0u);
+        tc_commit(&ctl->s_full[X]);
+      };
+      mbar_wait(&ctl->q_full, 0);
+      if (X == 1) mbar_wait(&ctl->s_free[0], 0);     // tile B starts a little after tile A: staggers the streams
+      int qk_stage = 0;
+      uint32_t qk_phase = 0;
+      mbar_wait(&ctl->kv_full[0], 0);
+      tc_fence_after_sync();
+      if (elect_one()) issue_qk(0);
+      __syncwarp();
+      if (++qk_stage == stages) { qk_stage = 0; qk_phase ^= 1; }
+      int stage = 0;
+      uint32_t pv_phase = 0;
+      for (int t = 0; t < T; ++t) {
+        const uint32_t par = (uint32_t)(t & 1);
+        // ---- next score tile as soon as this one sits in the softmax warps' registers ----
+        if (t + 1 < T) {
+          mbar_wait(&ctl->kv_full[qk_stage], qk_phase);
+          mbar_wait(&ctl->s_free[X], par);
+          tc_fence_after_sync();
+          if (elect_one()) issue_qk(qk_stage);
+          __syncwarp();
+          if (++qk_stage == stages) { qk_stage = 0; qk_phase ^= 1; }
+        }
+        // ---- O_X (+)= P_X[t] V_t ----
+        if (kOnes) mbar_wait(&ctl->v_ready[stage], pv_phase);
+        const uint32_t v_lo = ring_v_lo + (uint32_t)stage * kStageStep;
+        mbar_wait(&ctl->p_full[X], par);
+        tc_fence_after_sync();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kBlockN / 16; ++k)
+            tc_mma_ts_lh(o_tmem, p_tmem + k * 8, v_lo + k * 128, hi_kmaj, idesc_pv, (t > 0 || k > 0) ? 1u : 0u);
+          tc_commit(&ctl->pv_done[X][par]);
+          tc_commit(&ctl->kv_empty[stage]);
+        }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; pv_phase ^= 1; }
+      }
+    } else {
+      // ===================== ones column (kOnes): V[:, d] = 1 so that O[:, d] accumulates the row sums ============
+      if constexpr (kOnes) {
+        const uint32_t col_byte = (uint32_t)d * 2u;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = 0; t < T; ++t) {
+          mbar_wait(&ctl->kv_full[stage], phase);
+          uint8_t* vt = ring + stage * kStageBytes + kTileBytes;
+#pragma unroll
+          for (int r = (int)lane_id(); r < kBlockN; r += 32) {
+            const uint32_t off = (uint32_t)r * 128u + ((((col_byte >> 4) ^ ((uint32_t)r & 7u))) << 4) + (col_byte & 15u);
+            *reinterpret_cast<__half*>(vt + off) = __float2half_rn(1.0f);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane_id() == 0) mbar_arrive(&ctl->v_ready[stage]);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    warpgroup_reg_inc<104>();
+    // ===================== softmax streams: (tile X, key half H, lane quadrant) =====================
+    const int sid = warp - 4;
+    const int X = sid >> 3;
+    const int H = (sid >> 2) & 1;
+    const int quad = warp & 3;
+    const int row = quad * 32 + (int)lane_id();
+    const int bar_id = 1 + X * 4 + quad;                                      // the two warps that share these rows
+    const uint32_t t_lane = (uint32_t)(quad * 32) << 16;
+    const uint32_t s_addr = tmem_base + t_lane + (uint32_t)(X * kBlockN + H * 64);
+    const uint32_t p_addr = tmem_base + t_lane + kPCol + (uint32_t)(X * 64 + H * 32);
+    const uint32_t o_addr = tmem_base + t_lane + kOCol + (uint32_t)(X * 64);
+    const float sl2 = prm.scale_log2;
+    float m_run = 0.f;
+    float l_run = 0.f;
+    int slab_tile = 0;
+    for (int t = 0; t < T; ++t) {
+      const int valid = min(64, S - slab_tile * kBlockN - H * 64);
+      if (++slab_tile == tiles_per_slab) slab_tile = 0;
+      mbar_wait(&ctl->s_full[X], (uint32_t)(t & 1));
+      tc_fence_after_sync();
+      uint32_t v[2][32];
+      tmem_ld32(s_addr, v[0]);
+      tmem_ld32(s_addr + 32, v[1]);
+      tmem_wait_ld();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&ctl->s_free[X]);                        // S_X[t] is in registers: Q K^T of t+1 may run
+      if (valid < 64) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (32 * c + i >= valid) v[c][i] = 0xFF800000u;
+      }
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          mx[0] = fmax3(mx[0], __uint_as_float(v[c][i + 0]), __uint_as_float(v[c][i + 1]));
+          mx[1] = fmax3(mx[1], __uint_as_float(v[c][i + 2]), __uint_as_float(v[c][i + 3]));
+          mx[2] = fmax3(mx[2], __uint_as_float(v[c][i + 4]), __uint_as_float(v[c][i + 5]));
+          mx[3] = fmax3(mx[3], __uint_as_float(v[c][i + 6]), __uint_as_float(v[c][i + 7]));
+        }
+      const float mt_half = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      ctl->xch[t & 1][X][H][row] = mt_half;                                    // half-row max -> the row's other thread
+      named_bar_sync(bar_id, 64);
+      const float mt = fmaxf(mt_half, ctl->xch[t & 1][X][1 - H][row]);
+      const float mt_s = fmaxf(mt * sl2, -1.0e30f);
+      if (t == 0) {
+        m_run = mt_s;
+      } else {
+        const bool need = mt_s > m_run + kRescaleThreshold;                    // identical in both warps of the row
+        mbar_wait(&ctl->pv_done[X][(t - 1) & 1], (uint32_t)(((t - 1) >> 1) & 1));   // P V of t-1 retired: O_X quiescent,
+        tc_fence_after_sync();                                                      // the P region may be rewritten
+        if (__any_sync(0xffffffffu, need)) {
+          const float m_new = fmaxf(m_run, mt_s);
+          const float alpha = fast_exp2(m_run - m_new);
+          m_run = m_new;
+          l_run *= alpha;
+          for (int c0 = 16 * H; c0 < n_pv; c0 += 32) {                         // alternate 16-column chunks per half
+            uint32_t o[16];
+            tmem_ld16(o_addr + c0, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(o_addr + c0, o);
+          }
+          tmem_wait_st();
+        }
+      }
+      const float neg_m = -m_run;
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c <= 2; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (c < 2) {
+            float x0, x1;
+            ffma2(x0, x1, __uint_as_float(v[c][2 * i]), __uint_as_float(v[c][2 * i + 1]), sl2, neg_m);
+            v[c][2 * i] = __float_as_uint(poly_slot(2 * i, kPoly16) ? poly_exp2(x0) : fast_exp2(x0));
+            v[c][2 * i + 1] = __float_as_uint(poly_slot(2 * i + 1, kPoly16) ? poly_exp2(x1) : fast_exp2(x1));
+          }
+          if (c > 0) {
+            const float p0 = __uint_as_float(v[c - 1][2 * i]), p1 = __uint_as_float(v[c - 1][2 * i + 1]);
+            if (!kOnes) ls[i & 3] += p0 + p1;
+            pk[i] = pack_f16x2_rn(p0, p1);
+          }
+        }
+        if (c > 0) tmem_st16(p_addr + 16 * (c - 1), pk);
+      }
+      if (!kOnes) l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      tmem_wait_st();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&ctl->p_full[X]);
+    }
+    // ---- final: O / L -> fp16; the two halves write alternate 16-column chunks ----
+    mbar_wait(&ctl->pv_done[X][(T - 1) & 1], (uint32_t)(((T - 1) >> 1) & 1));
+    tc_fence_after_sync();
+    float l_tot;
+    if (kOnes) {
+      uint32_t lsum;
+      tmem_ld1(o_addr + d, lsum);
+      tmem_wait_ld();
+      l_tot = __uint_as_float(lsum);
+    } else {
+      ctl->xch[T & 1][X][H][row] = l_run;
+      named_bar_sync(bar_id, 64);
+      l_tot = l_run + ctl->xch[T & 1][X][1 - H][row];
+    }
+    const float inv_l = 1.0f / l_tot;
+    const int p_tok = m0 + X * kBlockM + row;
+    __half* orow = out + ((long long)smp.out_sample * prm.out_rows + (p_tok - prm.q_row0)) * prm.out_tok_stride + (long long)head * d;
+    for (int c0 = 16 * H; c0 < n_pv; c0 += 32) {
+      uint32_t o[16];
+      tmem_ld16(o_addr + c0, o);
+      tmem_wait_ld();
+      if (p_tok < prm.q_row_end) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (c0 + g * 8 < d) {
+            uint4 w;
+            w.x = pack_f16x2_rn(__uint_as_float(o[g * 8 + 0]) * inv_l, __uint_as_float(o[g * 8 + 1]) * inv_l);
+            w.y = pack_f16x2_rn(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l);
+            w.z = pack_f16x2_rn(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l);
+            w.w = pack_f16x2_rn(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + c0 + g * 8) = w;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int kPoly16, bool kOnes>
+int launch_q4s(const void* q, const void* k, const void* v, long long q_tok_stride, long long kv_tok_stride,
+               int q_samples_total, int kv_samples_total, const AttnTable& tab, int n_out, int S, int heads, int d,
+               float scale, void* out, int q_row0, int q_nrows, cudaStream_t stream) {
+  constexpr int kBlockN = 128;
+  constexpr int kQBytes = 2 * kBlockM * 128, kStageBytes = 2 * kBlockN * 128;
+  int stages = (227 * 1024 - 1024 - (int)sizeof(AttnCtl4s) - 64 - kQBytes) / kStageBytes;
+  if (stages > kPPStagesMax) stages = kPPStagesMax;
+  const size_t smem_bytes = 1024 + kQBytes + (size_t)stages * kStageBytes + sizeof(AttnCtl4s);
+  CUtensorMap map_q, map_k, map_v;
+  auto make = [&](CUtensorMap* m, const void* base, long long tok_stride, int samples, int box_rows) -> int {
+    const uint64_t dims[4] = {(uint64_t)d, (uint64_t)heads, (uint64_t)S, (uint64_t)samples};
+    const uint64_t strides[3] = {(uint64_t)d * 2, (uint64_t)tok_stride * 2, (uint64_t)S * tok_stride * 2};
+    const uint32_t box[4] = {64, 1, (uint32_t)box_rows, 1};
+    CUresult r = encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box,
+                              CU_TENSOR_MAP_SWIZZLE_128B);
+    if (r != CUDA_SUCCESS) { set_last_error("tf_ext_attn: cuTensorMapEncodeTiled failed: %d", (int)r); return TF_ERR_DRIVER; }
+    return TF_OK;
+  };
+  if (int e = make(&map_q, q, q_tok_stride, q_samples_total, kBlockM)) return e;
+  if (int e = make(&map_k, k, kv_tok_stride, kv_samples_total, kBlockN)) return e;
+  if (int e = make(&map_v, v, kv_tok_stride, kv_samples_total, kBlockN)) return e;
+  AttnParams prm;
+  prm.S = S; prm.heads = heads; prm.d = d; prm.n_out = n_out;
+  prm.q_row0 = q_row0; prm.q_row_end = (q_row0 + q_nrows < S) ? q_row0 + q_nrows : S; prm.out_rows = q_nrows;
+  prm.tiles_m = (prm.q_row_end - q_row0 + 2 * kBlockM - 1) / (2 * kBlockM);
+  prm.handoff = 0;
+  prm.stages = stages;
+  prm.scale_log2 = scale * 1.4426950408889634f;
+  prm.out_tok_stride = (long long)heads * d;
+  auto kern = ext_attn_q4s_kernel<kPoly16, kOnes>;
+  if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes),
+                 "tf_ext_attn smem attribute"))
+    return TF_ERR_CUDA;
+  const long long grid = (long long)n_out * heads * prm.tiles_m;
+  kern<<<(unsigned)grid, 640, smem_bytes, stream>>>(map_q, map_k, map_v, tab, prm, static_cast<__half*>(out));
+  return check_cuda(cudaGetLastError(), "tf_ext_attn launch");
+}
+
+// ================================================================================================
+// Quad-stream kernel for PAIRED samples ("q4d") — PnP q/k injection (reference tokenflow_utils.py:124-130).
+//
+// While t is in the injection schedule the uncond and the cond sample of a keyframe read the SAME q and the
+// SAME k (the source stream's): their score tiles and probabilities are identical, only V differs.  This
+// kernel computes S and P once per pair and multiplies P with [V_uncond | V_cond] in ONE tcgen05.mma per 16
+// keys: the two 64-column V tiles sit next to each other in shared memory, the MN-major B descriptor's
+// leading byte offset steps from one to the other, N = 64 + n_pv (112 at d = 40), and the accumulator holds
+// O_uncond in columns [0, 64) and O_cond in [64, 64 + n_pv).  Q K^T, the exp2 work, the MMA issue slots and the
+// K traffic are halved per output; the algorithmic FLOP count of the call is unchanged.
+// Structure: the shared-accumulator quad-stream kernel (two query tiles x two key halves, half-row maxima
+// exchanged per tile), fp16 P over the scores, P V before the next Q K^T.  Needs the ones column (d % 16 != 0).
+// TMEM (512 columns): S_A [0,128)  S_B [128,256)  O_A [256,384)  O_B [384,512).
+// ================================================================================================
+template <int kPoly16>
+__global__ void __launch_bounds__(640, 1)
+ext_attn_q4d_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                    const __grid_constant__ CUtensorMap map_v, const AttnPairTable tab, const AttnParams prm,
+                    __half* __restrict__ out) {
+  constexpr int kBlockN = 128;
+  constexpr int kQTileBytes = kBlockM * 128;
+  constexpr int kQBytes = 2 * kQTileBytes;
+  constexpr int kTileBytes = kBlockN * 128;
+  constexpr int kStageBytes = 3 * kTileBytes;              // K | V_uncond | V_cond
+  constexpr int kOCol = 256;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_smem = smem;
+  uint8_t* ring = smem + kQBytes;
+  AttnCtl4s* ctl = reinterpret_cast<AttnCtl4s*>(ring + prm.stages * kStageBytes);
+
+  const int S = prm.S, d = prm.d, stages = prm.stages;
+  const int per_sample = prm.heads * prm.tiles_m;
+  const int pair_slot = blockIdx.x / per_sample;
+  const int rem = blockIdx.x - pair_slot * per_sample;
+  const int head = rem / prm.tiles_m;
+  const int m0 = prm.q_row0 + (rem - head * prm.tiles_m) * (2 * kBlockM);
+  const AttnPair pr = tab.p[pair_slot];
+  const int tiles_per_slab = (S + kBlockN - 1) / kBlockN;
+  const int T = pr.n_kv * tiles_per_slab;
+  const int ksteps = (d + 15) / 16;
+  const int n_pv = ((d + 15) / 16) * 16;
+  const int n_acc = 64 + n_pv;                              // accumulator columns: [O_uncond (64) | O_cond (n_pv)]
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_v);
+    mbar_init(&ctl->q_full, 1);
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&ctl->kv_full[i], 1);
+      mbar_init(&ctl->kv_empty[i], 2);
+      mbar_init(&ctl->v_ready[i], 1);
+    }
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(&ctl->s_full[x], 1);
+      mbar_init(&ctl->p_full[x], 8);
+      mbar_init(&ctl->pv_done[x][0], 1);
+      mbar_init(&ctl->pv_done[x][1], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&ctl->tmem_base, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
+
+  if (warp < 4) {
+    warpgroup_reg_dec<64>();
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&ctl->q_full, (uint32_t)kQBytes);
+        tma_load_4d(q_smem, &map_q, &ctl->q_full, 0, head, m0, pr.q_sample);
+        tma_load_4d(q_smem + kQTileBytes, &map_q, &ctl->q_full, 0, head, m0 + kBlockM, pr.q_sample);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = 0; t < T; ++t) {
+          const int slab = t / tiles_per_slab;
+          const int n0 = (t - slab * tiles_per_slab) * kBlockN;
+          mbar_wait(&ctl->kv_empty[stage], phase ^ 1);
+          uint8_t* st = ring + stage * kStageBytes;
+          mbar_arrive_expect_tx(&ctl->kv_full[stage], (uint32_t)kStageBytes);
+          tma_load_4d(st, &map_k, &ctl->kv_full[stage], 0, head, n0, pr.k_sample0 + slab);
+          tma_load_4d(st + kTileBytes, &map_v, &ctl->kv_full[stage], 0, head, n0, pr.v_u0 + slab);
+          tma_load_4d(st + 2 * kTileBytes, &map_v, &ctl->kv_full[stage], 0, head, n0, pr.v_c0 + slab);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1 || warp == 2) {
+      // ===================== MMA issuers: one warp per query tile =====================
+      const int X = warp - 1;
+      const uint32_t idesc_qk = umma_idesc_f16(128, kBlockN, 0);
+      const uint32_t idesc_pv = umma_idesc_f16(128, (uint32_t)n_acc, 1);
+      constexpr uint32_t hi_kmaj = umma_desc_hi(1024);
+      const uint32_t q_lo = umma_desc_lo(smem_u32(q_smem + X * kQTileBytes), 16);
+      const uint32_t ring_k_lo = umma_desc_lo(smem_u32(ring), 16);
+      // B = [V_uncond | V_cond]: MN-major, the second 64 value columns start one tile (LBO) after the first
+      const uint32_t ring_v_lo = umma_desc_lo(smem_u32(ring + kTileBytes), kTileBytes);
+      constexpr uint32_t kStageStep = kStageBytes >> 4;
+      const uint32_t s_tmem = tmem_base + (uint32_t)(X * kBlockN);
+      const uint32_t o_tmem = tmem_base + kOCol + (uint32_t)(X * 128);
+      auto issue_qk = [&](int st) {
+        const uint32_t k_lo = ring_k_lo + (uint32_t)st * kStageStep;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          if (ks < ksteps) tc_mma_ss_lh(s_tmem, q_lo + ks * 2, hi_kmaj, k_lo + ks * 2, hi_kmaj, idesc_qk, ks > 0 ? 1u : 0u);
+        tc_commit(&ctl->s_full[X]);
+      };
+      mbar_wait(&ctl->q_full, 0);
+      if (X == 1) mbar_wait(&ctl->p_full[0], 0);      // tile B starts once tile A's first probabilities exist
+      int qk_stage = 0;
+      uint32_t qk_phase = 0;
+      mbar_wait(&ctl->kv_full[0], 0);
+      tc_fence_after_sync();
+      if (elect_one()) issue_qk(0);
+      __syncwarp();
+      if (++qk_stage == stages) { qk_stage = 0; qk_phase ^= 1; }
+      int stage = 0;
+      uint32_t pv_phase = 0;
+      for (int t = 0; t < T; ++t) {
+        const bool refill = t + 1 < T;
+        const uint32_t par = (uint32_t)(t & 1);
+        if (refill) mbar_wait(&ctl->kv_full[qk_stage], qk_phase);
+        mbar_wait(&ctl->v_ready[stage], pv_phase);
+        const uint32_t v_lo = ring_v_lo + (uint32_t)stage * kStageStep;
+        mbar_wait(&ctl->p_full[X], par);
+        tc_fence_after_sync();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)                  // [O_u | O_c] (+)= P_X[:, 16k..16k+15] [V_u | V_c][16k.., :]
+            tc_mma_ts_lh(o_tmem, s_tmem + (k < 4 ? k * 8 : 64 + (k - 4) * 8), v_lo + k * 128, hi_kmaj, idesc_pv,
+                         (t > 0 || k > 0) ? 1u : 0u);
+          tc_commit(&ctl->pv_done[X][par]);
+          tc_commit(&ctl->kv_empty[stage]);
+          if (refill) issue_qk(qk_stage);              // in order after the P V that consumes the P it overwrites
+        }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; pv_phase ^= 1; }
+        if (refill && ++qk_stage == stages) { qk_stage = 0; qk_phase ^= 1; }
+      }
+    } else {
+      // ===================== ones column: V_uncond[:, d] = 1 -> O[:, d] accumulates the (shared) row sums ===========
+      const uint32_t col_byte = (uint32_t)d * 2u;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < T; ++t) {
+        mbar_wait(&ctl->kv_full[stage], phase);
+        uint8_t* vt = ring + stage * kStageBytes + kTileBytes;
+#pragma unroll
+        for (int r = (int)lane_id(); r < kBlockN; r += 32) {
+          const uint32_t off = (uint32_t)r * 128u + ((((col_byte >> 4) ^ ((uint32_t)r & 7u))) << 4) + (col_byte & 15u);
+          *reinterpret_cast<__half*>(vt + off) = __float2half_rn(1.0f);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(&ctl->v_ready[stage]);
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    warpgroup_reg_inc<104>();
+    // ===================== softmax streams: (tile X, key half H, lane quadrant) =====================
+    const int sid = warp - 4;
+    const int X = sid >> 3;
+    const int H = (sid >> 2) & 1;
+    const int quad = warp & 3;
+    const int row = quad * 32 + (int)lane_id();
+    const int bar_id = 1 + X * 4 + quad;
+    const uint32_t t_lane = (uint32_t)(quad * 32) << 16;
+    const uint32_t s_addr = tmem_base + t_lane + (uint32_t)(X * kBlockN + H * 64);   // own 64 score columns; P at their start
+    const uint32_t o_addr = tmem_base + t_lane + kOCol + (uint32_t)(X * 128);
+    const float sl2 = prm.scale_log2;
+    float m_run = 0.f;
+    int slab_tile = 0;
+    for (int t = 0; t < T; ++t) {
+      const int valid = min(64, S - slab_tile * kBlockN - H * 64);
+      if (++slab_tile == tiles_per_slab) slab_tile = 0;
+      mbar_wait(&ctl->s_full[X], (uint32_t)(t & 1));
+      tc_fence_after_sync();
+      uint32_t v[2][32];
+      tmem_ld32(s_addr, v[0]);
+      tmem_ld32(s_addr + 32, v[1]);
+      tmem_wait_ld();
+      if (valid < 64) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (32 * c + i >= valid) v[c][i] = 0xFF800000u;
+      }
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          mx[0] = fmax3(mx[0], __uint_as_float(v[c][i + 0]), __uint_as_float(v[c][i + 1]));
+          mx[1] = fmax3(mx[1], __uint_as_float(v[c][i + 2]), __uint_as_float(v[c][i + 3]));
+          mx[2] = fmax3(mx[2], __uint_as_float(v[c][i + 4]), __uint_as_float(v[c][i + 5]));
+          mx[3] = fmax3(mx[3], __uint_as_float(v[c][i + 6]), __uint_as_float(v[c][i + 7]));
+        }
+      const float mt_half = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      ctl->xch[t & 1][X][H][row] = mt_half;
+      named_bar_sync(bar_id, 64);
+      const float mt = fmaxf(mt_half, ctl->xch[t & 1][X][1 - H][row]);
+      const float mt_s = fmaxf(mt * sl2, -1.0e30f);
+      if (t == 0) {
+        m_run = mt_s;
+      } else {
+        const bool need = mt_s > m_run + kRescaleThreshold;                    // identical in both warps of the row
+        if (__any_sync(0xffffffffu, need)) {
+          mbar_wait(&ctl->pv_done[X][(t - 1) & 1], (uint32_t)(((t - 1) >> 1) & 1));
+          tc_fence_after_sync();
+          const float m_new = fmaxf(m_run, mt_s);
+          const float alpha = fast_exp2(m_run - m_new);
+          m_run = m_new;
+          for (int c0 = 16 * H; c0 < n_acc; c0 += 32) {                        // alternate 16-column chunks per half
+            uint32_t o[16];
+            tmem_ld16(o_addr + c0, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(o_addr + c0, o);
+          }
+          tmem_wait_st();
+        }
+      }
+      const float neg_m = -m_run;
+#pragma unroll
+      for (int c = 0; c <= 2; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (c < 2) {
+            float x0, x1;
+            ffma2(x0, x1, __uint_as_float(v[c][2 * i]), __uint_as_float(v[c][2 * i + 1]), sl2, neg_m);
+            v[c][2 * i] = __float_as_uint(poly_slot(2 * i, kPoly16) ? poly_exp2(x0) : fast_exp2(x0));
+            v[c][2 * i + 1] = __float_as_uint(poly_slot(2 * i + 1, kPoly16) ? poly_exp2(x1) : fast_exp2(x1));
+          }
+          if (c > 0) pk[i] = pack_f16x2_rn(__uint_as_float(v[c - 1][2 * i]), __uint_as_float(v[c - 1][2 * i + 1]));
+        }
+        if (c > 0) tmem_st16(s_addr + 16 * (c - 1), pk);
+      }
+      tmem_wait_st();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&ctl->p_full[X]);
+    }
+    // ---- final: [O_u | O_c] / L -> fp16, the two halves write alternate 16-column chunks ----
+    mbar_wait(&ctl->pv_done[X][(T - 1) & 1], (uint32_t)(((T - 1) >> 1) & 1));
+    tc_fence_after_sync();
+    uint32_t lsum;
+    tmem_ld1(o_addr + d, lsum);
+    tmem_wait_ld();
+    const float inv_l = 1.0f / __uint_as_float(lsum);
+    const int p_tok = m0 + X * kBlockM + row;
+    for (int c0 = 16 * H; c0 < n_acc; c0 += 32) {
+      uint32_t o[16];
+      tmem_ld16(o_addr + c0, o);
+      tmem_wait_ld();
+      const int smp_out = c0 < 64 ? pr.out_u : pr.out_c;
+      const int col0 = c0 < 64 ? c0 : c0 - 64;
+      __half* orow = out + ((long long)smp_out * prm.out_rows + (p_tok - prm.q_row0)) * prm.out_tok_stride + (long long)head * d;
+      if (p_tok < prm.q_row_end) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (col0 + g * 8 < d) {
+            uint4 w;
+            w.x = pack_f16x2_rn(__uint_as_float(o[g * 8 + 0]) * inv_l, __uint_as_float(o[g * 8 + 1]) * inv_l);
+            w.y = pack_f16x2_rn(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l);
+            w.z = pack_f16x2_rn(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l);
+            w.w = pack_f16x2_rn(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + col0 + g * 8) = w;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int kPoly16>
+int launch_q4d(const void* q, const void* k, const void* v, long long q_tok_stride, long long kv_tok_stride,
+               int q_samples_total, int kv_samples_total, const AttnPairTable& tab, int n_pairs, int S, int heads, int d,
+               float scale, void* out, int q_row0, int q_nrows, cudaStream_t stream) {
+  constexpr int kBlockN = 128;
+  constexpr int kQBytes = 2 * kBlockM * 128, kStageBytes = 3 * kBlockN * 128;
+  int stages = (227 * 1024 - 1024 - (int)sizeof(AttnCtl4s) - 64 - kQBytes) / kStageBytes;
+  if (stages > kPPStagesMax) stages = kPPStagesMax;
+  const size_t smem_bytes = 1024 + kQBytes + (size_t)stages * kStageBytes + sizeof(AttnCtl4s);
+  CUtensorMap map_q, map_k, map_v;
+  auto make = [&](CUtensorMap* m, const void* base, long long tok_stride, int samples, int box_rows) -> int {
+    const uint64_t dims[4] = {(uint64_t)d, (uint64_t)heads, (uint64_t)S, (uint64_t)samples};
+    const uint64_t strides[3] = {(uint64_t)d * 2, (uint64_t)tok_stride * 2, (uint64_t)S * tok_stride * 2};
+    const uint32_t box[4] = {64, 1, (uint32_t)box_rows, 1};
+    CUresult r = encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box,
+                              CU_TENSOR_MAP_SWIZZLE_128B);
+    if (r != CUDA_SUCCESS) { set_last_error("tf_ext_attn: cuTensorMapEncodeTiled failed: %d", (int)r); return TF_ERR_DRIVER; }
+    return TF_OK;
+  };
+  if (int e = make(&map_q, q, q_tok_stride, q_samples_total, kBlockM)) return e;
+  if (int e = make(&map_k, k, kv_tok_stride, kv_samples_total, kBlockN)) return e;
+  if (int e = make(&map_v, v, kv_tok_stride, kv_samples_total, kBlockN)) return e;
+  AttnParams prm;
+  prm.S = S; prm.heads = heads; prm.d = d; prm.n_out = n_pairs;
+  prm.q_row0 = q_row0; prm.q_row_end = (q_row0 + q_nrows < S) ? q_row0 + q_nrows : S; prm.out_rows = q_nrows;
+  prm.tiles_m = (prm.q_row_end - q_row0 + 2 * kBlockM - 1) / (2 * kBlockM);
+  prm.handoff = 0;
+  prm.stages = stages;
+  prm.scale_log2 = scale * 1.4426950408889634f;
+  prm.out_tok_stride = (long long)heads * d;
+  auto kern = ext_attn_q4d_kernel<kPoly16>;
+  if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes),
+                 "tf_ext_attn smem attribute"))
+    return TF_ERR_CUDA;
+  const long long grid = (long long)n_pairs * heads * prm.tiles_m;
+  kern<<<(unsigned)grid, 640, smem_bytes, stream>>>(map_q, map_k, map_v, tab, prm, static_cast<__half*>(out));
+  return check_cuda(cudaGetLastError(), "tf_ext_attn (paired) launch");
+}
+
 template <int kDChunks, int kBlockN>
 int launch_cfg(const void* q, const void* k, const void* v, long long q_tok_stride, long long kv_tok_stride,
                int q_samples_total, int kv_samples_total, const AttnTable& tab, int n_out, int S, int heads, int d,
-               float scale, void* out, cudaStream_t stream) {
+               float scale, void* out, int q_row0, int q_nrows, cudaStream_t stream) {
   constexpr int kQBytes = kDChunks * kBlockM * 128;
   constexpr int kStageBytes = 2 * kDChunks * kBlockN * 128;
   int stages = (227 * 1024 - 2048 - kQBytes) / kStageBytes;
@@ -1162,7 +1867,8 @@ int launch_cfg(const void* q, const void* k, const void* v, long long q_tok_stri
 
   AttnParams prm;
   prm.S = S; prm.heads = heads; prm.d = d; prm.n_out = n_out;
-  prm.tiles_m = (S + kBlockM - 1) / kBlockM;
+  prm.q_row0 = q_row0; prm.q_row_end = (q_row0 + q_nrows < S) ? q_row0 + q_nrows : S; prm.out_rows = q_nrows;
+  prm.tiles_m = (prm.q_row_end - q_row0 + kBlockM - 1) / kBlockM;
   prm.stages = stages;
   prm.scale_log2 = scale * 1.4426950408889634f;
   prm.out_tok_stride = (long long)heads * d;
@@ -1180,60 +1886,104 @@ int launch_cfg(const void* q, const void* k, const void* v, long long q_tok_stri
 
 int launch_ext_attn(const void* q, const void* k, const void* v, long long q_tok_stride, long long kv_tok_stride,
                     int q_samples_total, int kv_samples_total, const AttnTable& tab, int n_out, int S, int heads,
-                    int d, float scale, void* out, cudaStream_t stream) {
-  if (n_out == 0 || S == 0) return TF_OK;
+                    int d, float scale, void* out, int q_row0, int q_nrows, cudaStream_t stream) {
+  if (n_out == 0 || S == 0 || q_nrows <= 0 || q_row0 >= S) return TF_OK;
+  const int rows = (q_row0 + q_nrows < S ? q_row0 + q_nrows : S) - q_row0;      // query rows this launch covers
   // A/B switches for profiling: TF_EXT_ATTN_MODE=v1 forces the one-query-tile kernel; TF_EXT_ATTN_POLY=<k> evaluates k
   // of every 16 exp2 on the FMA pipe; TF_EXT_ATTN_ONES=0/1 row sums in registers / by the tensor core.
   static const char* mode = getenv("TF_EXT_ATTN_MODE");
   static const char* env_poly = getenv("TF_EXT_ATTN_POLY");
   static const char* env_ones = getenv("TF_EXT_ATTN_ONES");
   const bool force_v1 = mode && mode[0] == 'v';
-  if (d <= 64 && S > 128 && !force_v1) {
+  if (d <= 64 && rows > 128 && !force_v1) {
     const bool can_ones = (d % 16) != 0;            // a zero-padded column inside the P V MMA's N exists
     const bool ones = can_ones && (env_ones ? atoi(env_ones) != 0 : kDefaultOnes);
     const bool pp = mode && mode[0] == 'p';         // TF_EXT_ATTN_MODE=pp: the ping-pong kernel (one stream per query tile)
     const int poly = env_poly ? atoi(env_poly) : (pp ? 0 : (ones ? kDefaultPolyOnes : kDefaultPoly));
 #define TF_PP(P, O)                                                                                              \
     return launch_pp<128, P, O>(q, k, v, q_tok_stride, kv_tok_stride, q_samples_total, kv_samples_total, tab, n_out, \
-                                S, heads, d, scale, out, stream)
+                                S, heads, d, scale, out, q_row0, q_nrows, stream)
 #define TF_Q4(P, O)                                                                                              \
     return launch_q4<P, O>(q, k, v, q_tok_stride, kv_tok_stride, q_samples_total, kv_samples_total, tab, n_out, S,  \
-                           heads, d, scale, out, stream)
+                           heads, d, scale, out, q_row0, q_nrows, stream)
     if (pp) {
       if (ones) { if (poly == 0) TF_PP(0, true); TF_PP(4, true); }
       if (poly == 0) TF_PP(0, false);
       TF_PP(4, false);
     }
-    if (ones) {
+    const bool q4s = mode && mode[0] == 'q' && mode[1] == '4' && mode[2] == 's';   // TF_EXT_ATTN_MODE=q4s: shared-accumulator variant
+    if (!q4s) {                                      // default: quad-stream kernel with split accumulators (measured fastest)
+      if (ones) {
+        switch (poly) {
+          case 0: TF_Q4(0, true);
+          case 2: TF_Q4(2, true);
+          case 4: TF_Q4(4, true);
+          default: TF_Q4(3, true);
+        }
+      }
       switch (poly) {
-        case 0: TF_Q4(0, true);
-        case 2: TF_Q4(2, true);
-        case 3: TF_Q4(3, true);
-        case 4: TF_Q4(4, true);
-        case 5: TF_Q4(5, true);
-        default: TF_Q4(6, true);
+        case 0: TF_Q4(0, false);
+        case 3: TF_Q4(3, false);
+        default: TF_Q4(4, false);
       }
     }
-    switch (poly) {
-      case 0: TF_Q4(0, false);
-      case 2: TF_Q4(2, false);
-      case 3: TF_Q4(3, false);
-      default: TF_Q4(4, false);
+#define TF_Q4S(P, O)                                                                                             \
+    return launch_q4s<P, O>(q, k, v, q_tok_stride, kv_tok_stride, q_samples_total, kv_samples_total, tab, n_out, S, \
+                            heads, d, scale, out, q_row0, q_nrows, stream)
+    if (ones) {
+      switch (poly) {
+        case 0: TF_Q4S(0, true);
+        case 4: TF_Q4S(4, true);
+        default: TF_Q4S(2, true);
+      }
     }
+    if (poly == 0) TF_Q4S(0, false);
+    TF_Q4S(3, false);
+#undef TF_Q4S
 #undef TF_PP
 #undef TF_Q4
   }
   if (d <= 64)
     return launch_cfg<1, 128>(q, k, v, q_tok_stride, kv_tok_stride, q_samples_total, kv_samples_total, tab, n_out,
-                              S, heads, d, scale, out, stream);
+                              S, heads, d, scale, out, q_row0, q_nrows, stream);
   if (d <= 128)
     return launch_cfg<2, 128>(q, k, v, q_tok_stride, kv_tok_stride, q_samples_total, kv_samples_total, tab, n_out,
-                              S, heads, d, scale, out, stream);
+                              S, heads, d, scale, out, q_row0, q_nrows, stream);
   if (d <= 192)
     return launch_cfg<3, 64>(q, k, v, q_tok_stride, kv_tok_stride, q_samples_total, kv_samples_total, tab, n_out,
-                             S, heads, d, scale, out, stream);
+                             S, heads, d, scale, out, q_row0, q_nrows, stream);
   set_last_error("tf_ext_attn: head dim %d > 192 is not supported", d);
   return TF_ERR_UNSUPPORTED;
+}
+
+// Paired samples (PnP q/k injection): S and P once per pair, P [V_u | V_c] in one MMA.  Returns TF_ERR_UNSUPPORTED for
+// shapes the paired kernel does not cover (the caller then launches the samples separately).
+bool ext_attn_pairs_supported(int rows, int d) {
+  static const char* env = getenv("TF_EXT_ATTN_DEDUP");
+  if (env && atoi(env) == 0) return false;
+  static const char* mode = getenv("TF_EXT_ATTN_MODE");
+  if (mode && (mode[0] == 'v' || mode[0] == 'p')) return false;
+  return d < 64 && (d % 16) != 0 && rows > 128;
+}
+
+int launch_ext_attn_pairs(const void* q, const void* k, const void* v, long long q_tok_stride, long long kv_tok_stride,
+                          int q_samples_total, int kv_samples_total, const AttnPairTable& tab, int n_pairs, int S,
+                          int heads, int d, float scale, void* out, int q_row0, int q_nrows, cudaStream_t stream) {
+  if (n_pairs == 0 || S == 0 || q_nrows <= 0 || q_row0 >= S) return TF_OK;
+  const int rows = (q_row0 + q_nrows < S ? q_row0 + q_nrows : S) - q_row0;
+  if (!ext_attn_pairs_supported(rows, d)) { set_last_error("tf_ext_attn: paired kernel does not cover S=%d d=%d", S, d); return TF_ERR_UNSUPPORTED; }
+  static const char* env_poly = getenv("TF_EXT_ATTN_POLY_PAIR");
+  const int poly = env_poly ? atoi(env_poly) : kDefaultPolyPair;
+#define TF_Q4D(P)                                                                                                \
+  return launch_q4d<P>(q, k, v, q_tok_stride, kv_tok_stride, q_samples_total, kv_samples_total, tab, n_pairs, S, heads, d, \
+                       scale, out, q_row0, q_nrows, stream)
+  switch (poly) {
+    case 0: TF_Q4D(0);
+    case 2: TF_Q4D(2);
+    case 4: TF_Q4D(4);
+    default: TF_Q4D(3);
+  }
+#undef TF_Q4D
 }
 
 #ifdef TF_TRACE

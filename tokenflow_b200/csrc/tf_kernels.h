@@ -49,8 +49,28 @@ struct AttnTable {
   AttnSample s[kMaxAttnSamples];
 };
 
+// One PAIR of output samples that share q and k and differ in v (PnP q/k injection: the uncond and the cond
+// sample of a keyframe, reference tokenflow_utils.py:124-130).
+constexpr int kMaxAttnPairs = 80;
+struct AttnPair {
+  int32_t out_u, out_c;      // output slabs of the two samples
+  int32_t q_sample;          // shared query slab
+  int32_t k_sample0;         // shared first key slab
+  int32_t v_u0, v_c0;        // first value slab of each sample
+  int32_t n_kv;
+};
+struct AttnPairTable {
+  AttnPair p[kMaxAttnPairs];
+};
+
+
+bool ext_attn_pairs_supported(int rows, int d);
+int launch_ext_attn_pairs(const void* q, const void* k, const void* v, long long q_tok_stride, long long kv_tok_stride,
+                          int q_samples_total, int kv_samples_total, const AttnPairTable& tab, int n_pairs, int S,
+                          int heads, int d, float scale, void* out, int q_row0, int q_nrows, cudaStream_t stream);
+
 int launch_ext_attn(const void* q, const void* k, const void* v, long long q_tok_stride, long long kv_tok_stride,
                     int q_samples_total, int kv_samples_total, const AttnTable& tab, int n_out, int S, int heads,
-                    int d, float scale, void* out, cudaStream_t stream);
+                    int d, float scale, void* out, int q_row0, int q_nrows, cudaStream_t stream);
 
 }  // namespace tf

@@ -69,6 +69,7 @@ class TokenFlowEditor(nn.Module):
         self._graph_pool = None
         self._g_static = None
         self._text_cache = {}
+        self._shard_cache = {}
 
     # ------------------------------------------------------------------------------------
     def init_method(self):
@@ -207,7 +208,7 @@ class TokenFlowEditor(nn.Module):
         src_all = self.source_latents_t(int(t))[indices].to(x.device, x.dtype)
         h.register_time(self, int(t))
         # ---- pivotal pass: this rank's m of the 3K (stream, keyframe) samples ----
-        shard = h.PivotalShard(G, r, K, self.group)
+        shard = h.PivotalShard(G, r, K, self.group, comm=self.comm, token_split=self.config.get("token_split", True))
         lat, emb = [], []
         for i in shard.slots:
             i = min(i, 3 * K - 1)                             # padding slots recompute the last sample
@@ -261,7 +262,11 @@ class TokenFlowEditor(nn.Module):
         G, r = self.world_size, self.rank
         if G == 1:
             return [divmod(i, K) for i in range(3 * K)], None
-        shard = self.hooks.PivotalShard(G, r, K, self.group, comm=self.comm)
+        key = (K, id(self.comm))
+        shard = self._shard_cache.get(key)
+        if shard is None:                     # one shard context per (K, communicator): it caches device index tensors
+            shard = self._shard_cache[key] = self.hooks.PivotalShard(G, r, K, self.group, comm=self.comm,
+                                                                     token_split=self.config.get("token_split", True))
         return [divmod(min(i, 3 * K - 1), K) for i in shard.slots], shard
 
     def _fused_text(self, slots, per):
@@ -404,6 +409,7 @@ class TokenFlowEditor(nn.Module):
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         events = [] if saved_timing is not None else None
+        launches0 = ops.launch_count() if ops is not None else 0
         if ops is not None:
             ops._timing = events                # per-launch EXTERNAL events recorded as graph nodes
         try:
@@ -414,7 +420,13 @@ class TokenFlowEditor(nn.Module):
                 ops._timing = saved_timing
         if self._graph_pool is None:
             self._graph_pool = graph.pool()
-        return {"graph": graph, "out": out, "events": events, "replays": 0}
+        return {"graph": graph, "out": out, "events": events, "replays": 0,
+                "launches": (ops.launch_count() - launches0) if ops is not None else 0}
+
+    def graph_launches_per_step(self) -> int:
+        """Kernels of this library inside one replay of the most recently used step graph."""
+        used = [e for e in self._graphs.values() if e["replays"]]
+        return max((e["launches"] for e in used), default=0)
 
     def graph_kernel_times(self):
         """{kernel: {"launches", "ms", "work"}} of the LAST replay of every captured variant that has been

@@ -52,6 +52,11 @@ _SIGNATURES = {
     "tf_ext_attn_fwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                        ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                        ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "tf_ext_attn_fwd_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int, _c_i32p,
+                                            _c_i32p, _c_i32p, _c_i32p, _c_i32p, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                            ctypes.c_void_p]),
     "tf_ext_attn_fwd_table": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p,
                                              ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int, _c_i32p,
                                              _c_i32p, _c_i32p, _c_i32p, _c_i32p, ctypes.c_int, ctypes.c_int,
@@ -344,21 +349,40 @@ class CudaOps:
             "tf_ext_attn_fwd"))
         return out
 
+    @staticmethod
+    def _slab_view(t: torch.Tensor):
+        """(tensor, token stride) of a [slabs, S, dim] fp16 operand the kernels can address in place: last dim
+        contiguous, slabs S tokens apart (a column slice of a packed [slabs, S, n*dim] buffer qualifies)."""
+        if t.dtype != torch.float16:
+            t = t.to(torch.float16)
+        S = t.shape[1]
+        if t.stride(2) != 1 or t.stride(1) % 8 or (t.shape[0] > 1 and t.stride(0) != S * t.stride(1)) \
+                or t.data_ptr() % 16:
+            t = t.contiguous()
+        return t, t.stride(1)
+
     def ext_attn_table(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, table, heads: int,
-                       scale: float) -> torch.Tensor:
+                       scale: float, row0: int = 0, nrows: Optional[int] = None) -> torch.Tensor:
         """General form (sharded pivotal pass): `table[j] = (q slab, first k slab, first v slab, number of
-        consecutive key slabs)` for output sample j.  q [Q,S,dim], k/v [KV,S,dim] fp16 → [len(table),S,dim]."""
+        consecutive key slabs)` for output sample j.  q [Q,S,dim], k/v [KV,S,dim] fp16 (column slices of packed
+        buffers are read in place) → [len(table), nrows, dim]: only the query tokens [row0, row0 + nrows) are
+        computed (default: all S; row0 a multiple of 128).  Rows past S stay unwritten."""
         _, S, dim = q.shape
         d = dim // heads
-        q, k, v = (t.to(torch.float16).contiguous() for t in (q, k, v))
+        nrows = S if nrows is None else int(nrows)
+        (q, q_tok), (k, k_tok), (v, v_tok) = self._slab_view(q), self._slab_view(k), self._slab_view(v)
+        if k_tok != v_tok:
+            k, v = k.contiguous(), v.contiguous()
+            k_tok = v_tok = dim
         n_out = len(table)
-        out = torch.empty((n_out, S, dim), dtype=torch.float16, device=q.device)
-        flops = sum(4.0 * S * (nkv * S) * dim for (_, _, _, nkv) in table)
-        self._timed("tf_ext_attn", flops, lambda: self._check(self.lib.tf_ext_attn_fwd_table(
-            q.data_ptr(), q.shape[0], dim, k.data_ptr(), v.data_ptr(), k.shape[0], dim, n_out,
+        out = torch.empty((n_out, nrows, dim), dtype=torch.float16, device=q.device)
+        rows_eff = max(0, min(S, row0 + nrows) - row0)
+        flops = sum(4.0 * rows_eff * (nkv * S) * dim for (_, _, _, nkv) in table)
+        self._timed("tf_ext_attn", flops, lambda: self._check(self.lib.tf_ext_attn_fwd_rows(
+            q.data_ptr(), q.shape[0], q_tok, k.data_ptr(), v.data_ptr(), k.shape[0], k_tok, n_out,
             _i32(range(n_out)), _i32([t[0] for t in table]), _i32([t[1] for t in table]),
-            _i32([t[2] for t in table]), _i32([t[3] for t in table]), S, heads, d, float(scale), out.data_ptr(),
-            self._stream()), "tf_ext_attn_fwd_table"))
+            _i32([t[2] for t in table]), _i32([t[3] for t in table]), S, heads, d, float(scale), int(row0), nrows,
+            out.data_ptr(), self._stream()), "tf_ext_attn_fwd_rows"))
         return out
 
 

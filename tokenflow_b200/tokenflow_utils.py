@@ -115,12 +115,27 @@ class PivotalShard:
     therefore reproduces the reference's [3K, S, dim] layout in its first 3K slabs.  Collectives go
     through torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU tests)."""
 
-    def __init__(self, world_size: int, rank: int, n_keyframes: int, group=None, comm=None):
+    def __init__(self, world_size: int, rank: int, n_keyframes: int, group=None, comm=None, token_split: bool = True):
         self.world_size, self.rank, self.K, self.group = world_size, rank, n_keyframes, group
+        # token_split: every rank computes the extended attention of ALL samples for its share of the query rows
+        # (exactly balanced, and paired q/k-injected samples stay together) instead of all rows of its own samples
+        self.token_split = bool(token_split)
         self.comm = comm                      # ops.Communicator (tf_allgather through the C ABI) or None
         self.m = -(-3 * n_keyframes // world_size)
         self.slots = list(range(rank * self.m, (rank + 1) * self.m))     # global sample ids (>= 3K: padding)
         self.n_collectives = 0
+        self._src_index = {}
+
+    def source_index(self, device) -> torch.Tensor:
+        """For each local slot, the global slot of the SOURCE-stream sample of the same keyframe (padding slots map
+        to themselves) — the gather index of the PnP conv injection (reference :86-91).  Built once per device and
+        kept (a CUDA-graph capture must not create host tensors)."""
+        key = str(device)
+        idx = self._src_index.get(key)
+        if idx is None:
+            idx = torch.tensor([i % self.K if i < 3 * self.K else i for i in self.slots], dtype=torch.int64).to(device)
+            self._src_index[key] = idx
+        return idx
 
     def all_gather(self, t: torch.Tensor) -> torch.Tensor:
         self.n_collectives += 1
@@ -131,6 +146,34 @@ class PivotalShard:
         out = torch.empty((self.world_size * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
         dist.all_gather_into_tensor(out, t, group=self.group)
         return out
+
+    def row_split(self, S: int):
+        """Query-token range [row0, row0 + nrows) of this rank when the extended attention of ALL 3K samples is
+        split by query rows (128-row tiles dealt evenly; trailing ranks may get rows past S = no work)."""
+        tiles = -(-S // 128)
+        nrows = -(-tiles // self.world_size) * 128
+        return self.rank * nrows, nrows
+
+    def global_attention_table(self, inject: bool):
+        """(q slab, first k slab, first v slab, key slabs) of all 3K samples in global slab coordinates
+        (reference :124-138): what every rank evaluates for its query rows after the q/k/v all-gather."""
+        K, tab = self.K, []
+        for i in range(3 * K):
+            s, f = divmod(i, K)
+            if s == 0:
+                tab.append((i, i, i, 1))
+            else:
+                tab.append((f if inject else i, 0 if inject else s * K, s * K, K))
+        return tab
+
+    def local_index(self, device) -> torch.Tensor:
+        """Global sample id of every local slot (padding slots repeat the last sample), as a device index."""
+        key = "local:" + str(device)
+        idx = self._src_index.get(key)
+        if idx is None:
+            idx = torch.tensor([min(i, 3 * self.K - 1) for i in self.slots], dtype=torch.int64).to(device)
+            self._src_index[key] = idx
+        return idx
 
     def attention_table(self, inject: bool):
         """Per local slot: (q slab, first k slab, first v slab, number of key slabs) in the coordinates of
@@ -281,7 +324,7 @@ def register_conv_injection(model, injection_schedule):
 
                 def inject_sharded(part, shard):   # sharded pivotal samples: the source sample may be remote
                     part_all = shard.all_gather(part)
-                    return part_all[[i % shard.K if i < 3 * shard.K else i for i in shard.slots]]
+                    return part_all.index_select(0, shard.source_index(part.device))
 
                 shard = getattr(res, "_tf_shard", None)
                 n_piv = getattr(res, "_tf_fused", 0)
@@ -324,6 +367,24 @@ def _fused_weight(attn, names, dtype):
     return hit[1]
 
 
+def _token_split_attention(attn, to_out, shard, q_all, k_all, v_all, inject):
+    """Extended attention of ALL 3K samples for this rank's query rows, `to_out` on those rows, all-gather, and
+    re-assembly of the complete [3K, S, dim] output (stashed on the module for the block); returns the rows of the
+    local samples."""
+    S, dim = q_all.shape[1], q_all.shape[2]
+    n_all = 3 * shard.K
+    row0, nrows = shard.row_split(S)
+    part = _ops().ext_attn_table(q_all, k_all, v_all, shard.global_attention_table(inject), attn.heads, attn.scale,
+                                 row0=row0, nrows=nrows)                       # [3K, nrows, dim]
+    if not torch.is_autocast_enabled() and part.dtype != to_out.weight.dtype:
+        part = part.to(to_out.weight.dtype)
+    part = to_out(part)
+    full = shard.all_gather(part).view(shard.world_size, n_all, nrows, dim).permute(1, 0, 2, 3)
+    full = full.reshape(n_all, shard.world_size * nrows, dim)[:, :S].contiguous()
+    attn._tf_attn_full = full
+    return full.index_select(0, shard.local_index(full.device))
+
+
 def _sa_forward(attn, pnp: bool):
     to_out = attn.to_out[0] if type(attn.to_out) is torch.nn.modules.container.ModuleList else attn.to_out
 
@@ -346,6 +407,18 @@ def _sa_forward(attn, pnp: bool):
                 qkv = torch.nn.functional.linear(x, _fused_weight(attn, ("to_q", "to_k", "to_v"), torch.float16))
                 q, k, v = qkv[..., :dim], qkv[..., dim:2 * dim], qkv[..., 2 * dim:]
                 out = _ops().ext_attn(q, k, v, attn.heads, attn.scale, inject)
+            elif shard.token_split:
+                # sharded pivotal pass, query rows split over the ranks: ONE all-gather of [q | k | v | pivot unit rows]
+                # per sample, attention of all 3K samples for this rank's query rows, to_out on those rows, ONE
+                # all-gather of the result (the block picks the complete [3K, S, dim] output up from the closure)
+                q = torch.nn.functional.linear(x, attn.to_q.weight.to(torch.float16))
+                kv = torch.nn.functional.linear(x, _fused_weight(attn, ("to_k", "to_v"), torch.float16))
+                unit = attn.__dict__.pop("_tf_unit_local", None)
+                packed = shard.all_gather(torch.cat([q, kv] + ([unit] if unit is not None else []), dim=-1))
+                if unit is not None:
+                    attn._tf_unit_gathered = packed[..., 3 * dim:]
+                return _token_split_attention(attn, to_out, shard, packed[..., :dim], packed[..., dim:2 * dim],
+                                              packed[..., 2 * dim:3 * dim], inject)
             else:
                 # sharded pivotal pass: ONE all-gather of [k | v | pivot unit rows] along the sample axis
                 # (+ one of q only while PnP-injecting, when the source stream's q lives on another rank)
@@ -365,6 +438,10 @@ def _sa_forward(attn, pnp: bool):
         v = attn.to_v(ctx)
         if shard is None:
             out = _ops().ext_attn(q, k, v, attn.heads, attn.scale, inject)
+        elif shard.token_split:
+            qkv_all = shard.all_gather(torch.cat([q, k, v], dim=-1))
+            return _token_split_attention(attn, to_out, shard, qkv_all[..., :dim], qkv_all[..., dim:2 * dim],
+                                          qkv_all[..., 2 * dim:], inject)
         else:                                    # keyframe K/V (and, when injecting, Q) all-gathered over NVLink
             k_all, v_all = shard.all_gather(k), shard.all_gather(v)
             q_src = shard.all_gather(q) if inject else q
@@ -476,7 +553,8 @@ def make_tokenflow_attention_block(block_class: Type[torch.nn.Module]) -> Type[t
                     self._tf_pivot_unit = unit_all[:shard.K]                              # source stream
                     self.pivot_hidden_states = norm_hidden_states
                     self.attn_output = self.attn1(norm_hidden_states, **cross_attention_kwargs)
-                self.kf_attn_output = shard.all_gather(self.attn_output)[:3 * shard.K]
+                full = self.attn1.__dict__.pop("_tf_attn_full", None)         # token-split closure: already complete
+                self.kf_attn_output = full if full is not None else shard.all_gather(self.attn_output)[:3 * shard.K]
             else:
                 n_frames = batch_size // 3
                 if fused_ln:

@@ -1,7 +1,8 @@
 #!/bin/bash
-# usage: gpu_multi.sh N
-N=$1
+# usage: gpu_multi.sh N [extra bench args]   — N-rank bench under torchrun, output in gpurun_out/
+N=$1; shift
 mkdir -p gpurun_out
+tag=${TAG:-n$N}
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
-   bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
-echo "exit $?"; tail -5 gpurun_out/bench_n$N.err; cut -c1-1800 gpurun_out/bench_n$N.json
+   bench.py --gpus $N "$@" > gpurun_out/r2_bench_$tag.json 2> gpurun_out/r2_bench_$tag.err
+echo "exit $? ($tag)"; grep -v "^W\|^$" gpurun_out/r2_bench_$tag.err | tail -4; cut -c1-2500 gpurun_out/r2_bench_$tag.json
