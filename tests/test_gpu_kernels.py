@@ -231,6 +231,9 @@ def _attn_ref(q, k, v, heads, scale, inject):
     (2, 200, 2, 40, False),      # SD1.5 top-level head dim, ragged key tiles
     (3, 256, 2, 40, True),
     (2, 160, 2, 80, False),
+    (3, 1024, 2, 80, True),      # SD1.5 middle level (two-half kernel), injected
+    (2, 300, 2, 128, False),     # widest head dim of the two-half kernel, ragged key tiles
+    (2, 384, 1, 96, False),
     (2, 96, 2, 160, True),
     (2, 144, 3, 64, False),      # SD2.1 head dim, 144 tokens
     (13, 16, 2, 16, True),       # K > 12 (the reference's per-frame loop path)

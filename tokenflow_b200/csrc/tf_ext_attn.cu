@@ -349,7 +349,7 @@ ext_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 // ================================================================================================
 constexpr int kPPStagesMax = 12;
 constexpr bool kDefaultOnes = true;        // measured choices (profiles/r02_ext_attn_variants.md)
-constexpr int kDefaultPolyOnes = 3, kDefaultPoly = 4, kDefaultPolyPair = 3;
+constexpr int kDefaultPolyOnes = 3, kDefaultPoly = 4, kDefaultPolyPair = 3, kDefaultPolyH2 = 3;
 struct AttnCtl2 {
   uint64_t q_full;
   uint64_t kv_full[kPPStagesMax];
@@ -1840,6 +1840,362 @@ int launch_q4d(const void* q, const void* k, const void* v, long long q_tok_stri
   return check_cuda(cudaGetLastError(), "tf_ext_attn (paired) launch");
 }
 
+// ================================================================================================
+// Two-half kernel for head dims 65..128 (SD1.5 middle level: d = 80): one 128-query tile per CTA, every key tile
+// split in two 64-key halves = two softmax streams, 8 softmax warps (two per SM sub-partition).
+//
+// The one-tile kernel at the top of this file ran d = 80 with 4 softmax warps (one per sub-partition, issue-bound:
+// profiles/r02_ext_attn_variants.md) and two tensor-memory passes per tile.  Here each thread keeps its 64 scores in
+// registers (one TMEM read), x*scale - max uses FFMA2, a fraction of the exp2 runs on the FMA pipe, and the two
+// halves own separate accumulators O_L / O_R (P V issued as 4 + 4 sixteen-key steps) merged once at the end.  The
+// score buffer is double-buffered: S[t+1] = Q K_{t+1}^T is issued right after P[t-1] V, so the tensor pipe works on
+// the next scores while the softmax warps are busy with the current ones (the per-tile tensor work, 640 cycles at
+// d = 80, is close to the exp2 work of a tile — neither side waits for the other).
+//   warp 0: TMA   warp 1: MMA issuer   warps 2,3: idle   warps 4-11: softmax (half, quadrant)
+// TMEM (512 columns): S[0] [0,128)  S[1] [128,256)  O_L [256,384)  O_R [384,512); fp16 P_L over S[b] columns
+// [0,32), P_R over [64,96).
+// ================================================================================================
+struct AttnCtlH2 {
+  uint64_t q_full;
+  uint64_t kv_full[8];
+  uint64_t kv_empty[8];
+  uint64_t s_full[2];          // [score buffer]
+  uint64_t p_full[2][2];       // [score buffer][half]
+  uint64_t pv_done[2][2];      // [half][t & 1]
+  uint64_t fin;
+  float2 ml_r[128];
+  uint32_t tmem_base;
+};
+
+template <int kDChunks, int kPoly16>
+__global__ void __launch_bounds__(384, 1)
+ext_attn_h2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                   const __grid_constant__ CUtensorMap map_v, const AttnTable tab, const AttnParams prm,
+                   __half* __restrict__ out) {
+  constexpr int kBlockN = 128;
+  constexpr int kQChunkBytes = kBlockM * 128;
+  constexpr int kKVChunkBytes = kBlockN * 128;
+  constexpr int kQBytes = kDChunks * kQChunkBytes;
+  constexpr int kTileBytes = kDChunks * kKVChunkBytes;
+  constexpr int kStageBytes = 2 * kTileBytes;
+  constexpr int kOCol = 256;
+  static_assert(kDChunks <= 2, "two 128-column accumulators");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_smem = smem;
+  uint8_t* ring = smem + kQBytes;
+  AttnCtlH2* ctl = reinterpret_cast<AttnCtlH2*>(ring + prm.stages * kStageBytes);
+
+  const int S = prm.S, d = prm.d, stages = prm.stages;
+  const int per_sample = prm.heads * prm.tiles_m;
+  const int sample_slot = blockIdx.x / per_sample;
+  const int rem = blockIdx.x - sample_slot * per_sample;
+  const int head = rem / prm.tiles_m;
+  const int m0 = prm.q_row0 + (rem - head * prm.tiles_m) * kBlockM;
+  const AttnSample smp = tab.s[sample_slot];
+  const int tiles_per_slab = (S + kBlockN - 1) / kBlockN;
+  const int T = smp.n_kv * tiles_per_slab;
+  const int ksteps = (d + 15) / 16;
+  const int n_pv = ((d + 15) / 16) * 16;
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_v);
+    mbar_init(&ctl->q_full, 1);
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&ctl->kv_full[i], 1);
+      mbar_init(&ctl->kv_empty[i], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&ctl->s_full[b], 1);
+      for (int hh = 0; hh < 2; ++hh) {
+        mbar_init(&ctl->p_full[b][hh], 4);
+        mbar_init(&ctl->pv_done[hh][b], 1);
+      }
+    }
+    mbar_init(&ctl->fin, 4);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&ctl->tmem_base, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&ctl->q_full, (uint32_t)kQBytes);
+#pragma unroll
+      for (int c = 0; c < kDChunks; ++c)
+        tma_load_4d(q_smem + c * kQChunkBytes, &map_q, &ctl->q_full, c * 64, head, m0, smp.q_sample);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < T; ++t) {
+        const int slab = t / tiles_per_slab;
+        const int n0 = (t - slab * tiles_per_slab) * kBlockN;
+        mbar_wait(&ctl->kv_empty[stage], phase ^ 1);
+        uint8_t* st = ring + stage * kStageBytes;
+        mbar_arrive_expect_tx(&ctl->kv_full[stage], (uint32_t)kStageBytes);
+#pragma unroll
+        for (int c = 0; c < kDChunks; ++c) {
+          tma_load_4d(st + c * kKVChunkBytes, &map_k, &ctl->kv_full[stage], c * 64, head, n0, smp.k_sample0 + slab);
+          tma_load_4d(st + kTileBytes + c * kKVChunkBytes, &map_v, &ctl->kv_full[stage], c * 64, head, n0,
+                      smp.v_sample0 + slab);
+        }
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc_qk = umma_idesc_f16(128, kBlockN, 0);
+    const uint32_t idesc_pv = umma_idesc_f16(128, (uint32_t)n_pv, 1);
+    constexpr uint32_t hi_kmaj = umma_desc_hi(1024);
+    const uint32_t q_lo = umma_desc_lo(smem_u32(q_smem), 16);
+    const uint32_t ring_k_lo = umma_desc_lo(smem_u32(ring), 16);
+    const uint32_t ring_v_lo = umma_desc_lo(smem_u32(ring + kTileBytes), kKVChunkBytes);     // LBO: next 64 value columns
+    constexpr uint32_t kStageStep = kStageBytes >> 4;
+    constexpr uint32_t kQChunkStep = kQChunkBytes >> 4, kKChunkStep = kKVChunkBytes >> 4;
+    const uint32_t o_l = tmem_base + kOCol, o_r = tmem_base + kOCol + 128;
+    auto issue_qk = [&](int t, int st) {            // S[t & 1] = Q K_t^T
+      const uint32_t k_lo = ring_k_lo + (uint32_t)st * kStageStep;
+      const uint32_t s_tmem = tmem_base + (uint32_t)((t & 1) * kBlockN);
+#pragma unroll
+      for (int ks = 0; ks < 4 * kDChunks; ++ks)
+        if (ks < ksteps)
+          tc_mma_ss_lh(s_tmem, q_lo + (ks >> 2) * kQChunkStep + (ks & 3) * 2, hi_kmaj,
+                       k_lo + (ks >> 2) * kKChunkStep + (ks & 3) * 2, hi_kmaj, idesc_qk, ks > 0 ? 1u : 0u);
+      tc_commit(&ctl->s_full[t & 1]);
+    };
+    mbar_wait(&ctl->q_full, 0);
+    mbar_wait(&ctl->kv_full[0], 0);
+    tc_fence_after_sync();
+    if (elect_one()) issue_qk(0, 0);
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = 0; t < T; ++t) {
+      int nstage = stage + 1;
+      uint32_t nphase = phase;
+      if (nstage == stages) { nstage = 0; nphase ^= 1; }
+      const int b = t & 1;
+      const uint32_t par = (uint32_t)((t >> 1) & 1);
+      if (t + 1 < T) {                              // next score tile first: it overlaps the softmax of this one.  In
+        mbar_wait(&ctl->kv_full[nstage], nphase);   // order after P V of t-1, which read the P this Q K^T overwrites.
+        tc_fence_after_sync();
+        if (elect_one()) issue_qk(t + 1, nstage);
+        __syncwarp();
+      }
+      const uint32_t v_lo = ring_v_lo + (uint32_t)stage * kStageStep;
+      const uint32_t p_tmem = tmem_base + (uint32_t)(b * kBlockN);
+      mbar_wait(&ctl->p_full[b][0], par);
+      tc_fence_after_sync();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_ts_lh(o_l, p_tmem + k * 8, v_lo + k * 128, hi_kmaj, idesc_pv, (t > 0 || k > 0) ? 1u : 0u);
+        tc_commit(&ctl->pv_done[0][b]);
+      }
+      __syncwarp();
+      mbar_wait(&ctl->p_full[b][1], par);
+      tc_fence_after_sync();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_ts_lh(o_r, p_tmem + 64 + k * 8, v_lo + (4 + k) * 128, hi_kmaj, idesc_pv, (t > 0 || k > 0) ? 1u : 0u);
+        tc_commit(&ctl->pv_done[1][b]);
+        tc_commit(&ctl->kv_empty[stage]);
+      }
+      __syncwarp();
+      stage = nstage;
+      phase = nphase;
+    }
+  } else if (warp >= 4) {
+    // ===================== softmax streams: (key half H, lane quadrant) =====================
+    const int H = (warp - 4) >> 2;
+    const int quad = warp & 3;
+    const int row = quad * 32 + (int)lane_id();
+    const uint32_t t_lane = (uint32_t)(quad * 32) << 16;
+    const uint32_t o_addr = tmem_base + t_lane + kOCol + (uint32_t)(H * 128);
+    const float sl2 = prm.scale_log2;
+    float m_run = 0.f;
+    float l_run = 0.f;
+    int slab_tile = 0;
+    for (int t = 0; t < T; ++t) {
+      const int b = t & 1;
+      const uint32_t par = (uint32_t)((t >> 1) & 1);
+      const int valid = min(64, S - slab_tile * kBlockN - H * 64);
+      if (++slab_tile == tiles_per_slab) slab_tile = 0;
+      const uint32_t s_addr = tmem_base + t_lane + (uint32_t)(b * kBlockN + H * 64);
+      mbar_wait(&ctl->s_full[b], par);
+      tc_fence_after_sync();
+      uint32_t v[2][32];
+      tmem_ld32(s_addr, v[0]);
+      tmem_ld32(s_addr + 32, v[1]);
+      tmem_wait_ld();
+      if (valid < 64) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (32 * c + i >= valid) v[c][i] = 0xFF800000u;
+      }
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          mx[0] = fmax3(mx[0], __uint_as_float(v[c][i + 0]), __uint_as_float(v[c][i + 1]));
+          mx[1] = fmax3(mx[1], __uint_as_float(v[c][i + 2]), __uint_as_float(v[c][i + 3]));
+          mx[2] = fmax3(mx[2], __uint_as_float(v[c][i + 4]), __uint_as_float(v[c][i + 5]));
+          mx[3] = fmax3(mx[3], __uint_as_float(v[c][i + 6]), __uint_as_float(v[c][i + 7]));
+        }
+      const float mt_s = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sl2, -1.0e30f);
+      if (t == 0) {
+        m_run = mt_s;
+      } else {
+        const bool need = mt_s > m_run + kRescaleThreshold;
+        if (__any_sync(0xffffffffu, need)) {
+          mbar_wait(&ctl->pv_done[H][(t - 1) & 1], (uint32_t)(((t - 1) >> 1) & 1));
+          tc_fence_after_sync();
+          const float m_new = fmaxf(m_run, mt_s);
+          const float alpha = fast_exp2(m_run - m_new);
+          m_run = m_new;
+          l_run *= alpha;
+          for (int c0 = 0; c0 < n_pv; c0 += 16) {
+            uint32_t o[16];
+            tmem_ld16(o_addr + c0, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(o_addr + c0, o);
+          }
+          tmem_wait_st();
+        }
+      }
+      const float neg_m = -m_run;
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c <= 2; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (c < 2) {
+            float x0, x1;
+            ffma2(x0, x1, __uint_as_float(v[c][2 * i]), __uint_as_float(v[c][2 * i + 1]), sl2, neg_m);
+            v[c][2 * i] = __float_as_uint(poly_slot(2 * i, kPoly16) ? poly_exp2(x0) : fast_exp2(x0));
+            v[c][2 * i + 1] = __float_as_uint(poly_slot(2 * i + 1, kPoly16) ? poly_exp2(x1) : fast_exp2(x1));
+          }
+          if (c > 0) {
+            const float p0 = __uint_as_float(v[c - 1][2 * i]), p1 = __uint_as_float(v[c - 1][2 * i + 1]);
+            ls[i & 3] += p0 + p1;
+            pk[i] = pack_f16x2_rn(p0, p1);
+          }
+        }
+        if (c > 0) tmem_st16(s_addr + 16 * (c - 1), pk);
+      }
+      l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      tmem_wait_st();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&ctl->p_full[b][H]);
+    }
+    // ---- final merge of the two key halves of a row ----
+    mbar_wait(&ctl->pv_done[H][(T - 1) & 1], (uint32_t)(((T - 1) >> 1) & 1));
+    tc_fence_after_sync();
+    if (H == 1) {
+      ctl->ml_r[row] = make_float2(m_run, l_run);
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&ctl->fin);
+    } else {
+      mbar_wait(&ctl->pv_done[1][(T - 1) & 1], (uint32_t)(((T - 1) >> 1) & 1));
+      mbar_wait(&ctl->fin, 0);
+      tc_fence_after_sync();
+      const float2 mr = ctl->ml_r[row];
+      const float m = fmaxf(m_run, mr.x);
+      const float a_l = fast_exp2(m_run - m), a_r = fast_exp2(mr.x - m);
+      const float inv_l = 1.0f / (a_l * l_run + a_r * mr.y);
+      const float w_l = a_l * inv_l, w_r = a_r * inv_l;
+      const int p_tok = m0 + row;
+      __half* orow = out + ((long long)smp.out_sample * prm.out_rows + (p_tok - prm.q_row0)) * prm.out_tok_stride + (long long)head * d;
+      for (int c0 = 0; c0 < n_pv; c0 += 16) {
+        uint32_t ol[16], orr[16];
+        tmem_ld16(o_addr + c0, ol);
+        tmem_ld16(o_addr + 128 + c0, orr);
+        tmem_wait_ld();
+        if (p_tok < prm.q_row_end) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            if (c0 + g * 8 < d) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                f[e] = fmaf(w_l, __uint_as_float(ol[g * 8 + e]), w_r * __uint_as_float(orr[g * 8 + e]));
+              uint4 w;
+              w.x = pack_f16x2_rn(f[0], f[1]);
+              w.y = pack_f16x2_rn(f[2], f[3]);
+              w.z = pack_f16x2_rn(f[4], f[5]);
+              w.w = pack_f16x2_rn(f[6], f[7]);
+              *reinterpret_cast<uint4*>(orow + c0 + g * 8) = w;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int kDChunks, int kPoly16>
+int launch_h2(const void* q, const void* k, const void* v, long long q_tok_stride, long long kv_tok_stride,
+              int q_samples_total, int kv_samples_total, const AttnTable& tab, int n_out, int S, int heads, int d,
+              float scale, void* out, int q_row0, int q_nrows, cudaStream_t stream) {
+  constexpr int kBlockN = 128;
+  constexpr int kQBytes = kDChunks * kBlockM * 128;
+  constexpr int kStageBytes = 2 * kDChunks * kBlockN * 128;
+  int stages = (227 * 1024 - 1024 - (int)sizeof(AttnCtlH2) - 64 - kQBytes) / kStageBytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) { set_last_error("tf_ext_attn: configuration does not fit shared memory"); return TF_ERR_UNSUPPORTED; }
+  const size_t smem_bytes = 1024 + kQBytes + (size_t)stages * kStageBytes + sizeof(AttnCtlH2);
+  CUtensorMap map_q, map_k, map_v;
+  auto make = [&](CUtensorMap* m, const void* base, long long tok_stride, int samples, int box_rows) -> int {
+    const uint64_t dims[4] = {(uint64_t)d, (uint64_t)heads, (uint64_t)S, (uint64_t)samples};
+    const uint64_t strides[3] = {(uint64_t)d * 2, (uint64_t)tok_stride * 2, (uint64_t)S * tok_stride * 2};
+    const uint32_t box[4] = {64, 1, (uint32_t)box_rows, 1};
+    CUresult r = encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box,
+                              CU_TENSOR_MAP_SWIZZLE_128B);
+    if (r != CUDA_SUCCESS) { set_last_error("tf_ext_attn: cuTensorMapEncodeTiled failed: %d", (int)r); return TF_ERR_DRIVER; }
+    return TF_OK;
+  };
+  if (int e = make(&map_q, q, q_tok_stride, q_samples_total, kBlockM)) return e;
+  if (int e = make(&map_k, k, kv_tok_stride, kv_samples_total, kBlockN)) return e;
+  if (int e = make(&map_v, v, kv_tok_stride, kv_samples_total, kBlockN)) return e;
+  AttnParams prm;
+  prm.S = S; prm.heads = heads; prm.d = d; prm.n_out = n_out;
+  prm.q_row0 = q_row0; prm.q_row_end = (q_row0 + q_nrows < S) ? q_row0 + q_nrows : S; prm.out_rows = q_nrows;
+  prm.tiles_m = (prm.q_row_end - q_row0 + kBlockM - 1) / kBlockM;
+  prm.handoff = 0;
+  prm.stages = stages;
+  prm.scale_log2 = scale * 1.4426950408889634f;
+  prm.out_tok_stride = (long long)heads * d;
+  auto kern = ext_attn_h2_kernel<kDChunks, kPoly16>;
+  if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes),
+                 "tf_ext_attn smem attribute"))
+    return TF_ERR_CUDA;
+  const long long grid = (long long)n_out * heads * prm.tiles_m;
+  kern<<<(unsigned)grid, 384, smem_bytes, stream>>>(map_q, map_k, map_v, tab, prm, static_cast<__half*>(out));
+  return check_cuda(cudaGetLastError(), "tf_ext_attn launch");
+}
+
 template <int kDChunks, int kBlockN>
 int launch_cfg(const void* q, const void* k, const void* v, long long q_tok_stride, long long kv_tok_stride,
                int q_samples_total, int kv_samples_total, const AttnTable& tab, int n_out, int S, int heads, int d,
@@ -1946,6 +2302,20 @@ int launch_ext_attn(const void* q, const void* k, const void* v, long long q_tok
   if (d <= 64)
     return launch_cfg<1, 128>(q, k, v, q_tok_stride, kv_tok_stride, q_samples_total, kv_samples_total, tab, n_out,
                               S, heads, d, scale, out, q_row0, q_nrows, stream);
+  if (d <= 128 && !force_v1) {                   // SD1.5 middle level (d = 80): two-half kernel
+    static const char* env_poly_h2 = getenv("TF_EXT_ATTN_POLY_H2");
+    const int poly = env_poly_h2 ? atoi(env_poly_h2) : kDefaultPolyH2;
+#define TF_H2(P)                                                                                                 \
+    return launch_h2<2, P>(q, k, v, q_tok_stride, kv_tok_stride, q_samples_total, kv_samples_total, tab, n_out, S,  \
+                           heads, d, scale, out, q_row0, q_nrows, stream)
+    switch (poly) {
+      case 0: TF_H2(0);
+      case 2: TF_H2(2);
+      case 4: TF_H2(4);
+      default: TF_H2(3);
+    }
+#undef TF_H2
+  }
   if (d <= 128)
     return launch_cfg<2, 128>(q, k, v, q_tok_stride, kv_tok_stride, q_samples_total, kv_samples_total, tab, n_out,
                               S, heads, d, scale, out, q_row0, q_nrows, stream);
