@@ -378,6 +378,86 @@ def test_edit_with_strict_dtype(monkeypatch):
 
 
 # ------------------------------------------------------------------------------------------------
+# the sharded CUDA path on ONE GPU: two "ranks" as two threads with an in-process all-gather
+# ------------------------------------------------------------------------------------------------
+class _ThreadWorld:
+    """In-process stand-in for the communicator: rank threads meet at a barrier and concatenate their tensors
+    (all ranks enqueue on the same default CUDA stream, so stream order makes the producers visible)."""
+
+    def __init__(self, world):
+        import threading
+        self.world = world
+        self.barrier = threading.Barrier(world, timeout=300)
+        self.slots = [None] * world
+
+    class _Rank:
+        def __init__(self, parent, rank):
+            self.parent, self.rank = parent, rank
+
+        def all_gather(self, t):
+            P = self.parent
+            P.slots[self.rank] = t.contiguous()
+            P.barrier.wait()
+            out = torch.cat(list(P.slots))
+            P.barrier.wait()
+            return out
+
+    def rank(self, r):
+        return _ThreadWorld._Rank(self, r)
+
+
+@pytest.mark.parametrize("token_split", [True, False])
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_cuda_path_in_one_process(world, token_split):
+    """The multi-GPU code path of the hooks on the CUDA kernels (packed q|k|v|unit gather, query-row split of the
+    extended attention with the paired kernel, output re-assembly, sharded conv injection) with `world` rank threads
+    on one GPU == the single-rank edit."""
+    import threading
+    steps, n_frames, batch = 4, 8, 2
+
+    def edit(world_size, rank, comm, out):
+        try:
+            unet = sd_unet.build_unet("tiny", seed=1, device="cuda", dtype=torch.float16)
+            cfg = {"n_frames": n_frames, "batch_size": batch, "n_timesteps": steps, "guidance_scale": 7.5, "mode": "pnp",
+                   "pnp_attn_t": 0.5, "pnp_f_t": 0.8, "fused_pass": True, "cuda_graph": False, "keyframe_seed": 1,
+                   "token_split": token_split}
+            x, text, pnp, src = synthetic_inputs(n_frames, 16, unet.config.cross_attention_dim, steps, seed=1,
+                                                 device="cuda", dtype=torch.float16, ctx_len=7)
+            ed = TokenFlowEditor(unet, DDIMScheduler(), tfu, cfg, text, pnp, source_latents=lambda t: src[t],
+                                 world_size=world_size, rank=rank)
+            if comm is not None:
+                ed.attach_communicator(comm)
+            ed.init_method()
+            out[rank] = (ed.sample_loop(x).float(), ed.keyframe_log)
+        except BaseException as ex:  # noqa: BLE001
+            out[rank] = ex
+            if comm is not None:
+                comm.parent.barrier.abort()
+
+    tfu._install_ops_for_testing(None)
+    tfu._ops()                                              # one op object for all threads
+    ref = {}
+    edit(1, 0, None, ref)
+    assert not isinstance(ref[0], BaseException), ref[0]
+    want, kf_want = ref[0]
+    tw = _ThreadWorld(world)
+    res = {}
+    threads = [threading.Thread(target=edit, args=(world, r, tw.rank(r), res)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=600)
+    for r in range(world):
+        assert r in res and not isinstance(res[r], BaseException), res.get(r)
+        got, kf = res[r]
+        assert kf == kf_want
+        assert torch.isfinite(got).all()
+        rel = ((got - want).norm() / want.norm()).item()
+        assert rel < 2e-2, (r, rel)
+    assert torch.equal(res[0][0], res[1][0])               # every rank ends the step with the same latents
+
+
+# ------------------------------------------------------------------------------------------------
 # NCCL: two ranks on two GPUs == one rank  (skipped with fewer than two GPUs)
 # ------------------------------------------------------------------------------------------------
 _WORKER = r"""

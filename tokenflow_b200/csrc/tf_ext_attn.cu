@@ -350,6 +350,7 @@ ext_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 constexpr int kPPStagesMax = 12;
 constexpr bool kDefaultOnes = true;        // measured choices (profiles/r02_ext_attn_variants.md)
 constexpr int kDefaultPolyOnes = 3, kDefaultPoly = 4, kDefaultPolyPair = 3, kDefaultPolyH2 = 3;
+constexpr bool kDefaultOneTile = false;
 struct AttnCtl2 {
   uint64_t q_full;
   uint64_t kv_full[kPPStagesMax];
@@ -790,17 +791,22 @@ __device__ __forceinline__ void ffma2(float& y0, float& y1, float a0, float a1, 
   asm("mov.b64 {%0, %1}, %2;" : "=f"(y0), "=f"(y1) : "l"(rd));
 }
 
-template <int kPoly16, bool kOnes>
-__global__ void __launch_bounds__(640, 1)
+// kTiles = 2: two query tiles per CTA, one CTA per SM (640 threads, all 512 TMEM columns).
+// kTiles = 1: one query tile per CTA, TWO independent CTAs per SM (384 threads, 256 TMEM columns, two smem stages each):
+//             the two tiles' streams are then not coupled through a shared K/V ring and drift out of phase instead
+//             of running their exp2 phases and their score round trips in lockstep.
+template <int kPoly16, bool kOnes, int kTiles>
+__global__ void __launch_bounds__(kTiles == 2 ? 640 : 384, kTiles == 2 ? 1 : 2)
 ext_attn_q4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                    const __grid_constant__ CUtensorMap map_v, const AttnTable tab, const AttnParams prm,
                    __half* __restrict__ out) {
   constexpr int kBlockN = 128;
   constexpr int kQTileBytes = kBlockM * 128;
-  constexpr int kQBytes = 2 * kQTileBytes;
+  constexpr int kQBytes = kTiles * kQTileBytes;
   constexpr int kTileBytes = kBlockN * 128;
   constexpr int kStageBytes = 2 * kTileBytes;
-  constexpr int kOCol = 256;
+  constexpr int kOCol = kTiles * 128;                         // accumulators start after the score buffers
+  constexpr uint32_t kTmemCols = kTiles * 256;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -813,7 +819,7 @@ ext_attn_q4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   const int sample_slot = blockIdx.x / per_sample;
   const int rem = blockIdx.x - sample_slot * per_sample;
   const int head = rem / prm.tiles_m;
-  const int m0 = prm.q_row0 + (rem - head * prm.tiles_m) * (2 * kBlockM);
+  const int m0 = prm.q_row0 + (rem - head * prm.tiles_m) * (kTiles * kBlockM);
   const AttnSample smp = tab.s[sample_slot];
   const int tiles_per_slab = (S + kBlockN - 1) / kBlockN;
   const int T = smp.n_kv * tiles_per_slab;
@@ -828,7 +834,7 @@ ext_attn_q4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     mbar_init(&ctl->q_full, 1);
     for (int i = 0; i < stages; ++i) {
       mbar_init(&ctl->kv_full[i], 1);
-      mbar_init(&ctl->kv_empty[i], 2);
+      mbar_init(&ctl->kv_empty[i], kTiles);
       mbar_init(&ctl->v_ready[i], 1);
     }
     for (int x = 0; x < 2; ++x) {
@@ -842,20 +848,20 @@ ext_attn_q4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(&ctl->tmem_base, 512);
+  if (warp == 1) tmem_alloc(&ctl->tmem_base, kTmemCols);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
 
   if (warp < 4) {
-    warpgroup_reg_dec<64>();
+    warpgroup_reg_dec<(kTiles == 2 ? 64 : 56)>();
     if (warp == 0) {
       // ===================== TMA producer =====================
       if (elect_one()) {
         mbar_arrive_expect_tx(&ctl->q_full, (uint32_t)kQBytes);
         tma_load_4d(q_smem, &map_q, &ctl->q_full, 0, head, m0, smp.q_sample);
-        tma_load_4d(q_smem + kQTileBytes, &map_q, &ctl->q_full, 0, head, m0 + kBlockM, smp.q_sample);
+        if (kTiles == 2) tma_load_4d(q_smem + kQTileBytes, &map_q, &ctl->q_full, 0, head, m0 + kBlockM, smp.q_sample);
         int stage = 0;
         uint32_t phase = 0;
         for (int t = 0; t < T; ++t) {
@@ -869,7 +875,7 @@ ext_attn_q4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
-    } else if (warp == 1 || warp == 2) {
+    } else if (warp == 1 || (warp == 2 && kTiles == 2)) {
       // ===================== MMA issuers: one warp per query tile (warp 1 -> A, warp 2 -> B) ==============
       const int X = warp - 1;
       const uint32_t idesc_qk = umma_idesc_f16(128, kBlockN, 0);
@@ -891,7 +897,7 @@ ext_attn_q4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       };
       mbar_wait(&ctl->q_full, 0);
       // tile B starts once the first half of tile A's first probabilities exists: staggers the streams
-      if (X == 1) mbar_wait(&ctl->p_full[0][0], 0);
+      if (kTiles == 2 && X == 1) mbar_wait(&ctl->p_full[0][0], 0);
       int qk_stage = 0;
       uint32_t qk_phase = 0;
       mbar_wait(&ctl->kv_full[0], 0);
@@ -930,7 +936,7 @@ ext_attn_q4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         if (++stage == stages) { stage = 0; pv_phase ^= 1; }
         if (refill && ++qk_stage == stages) { qk_stage = 0; qk_phase ^= 1; }
       }
-    } else {
+    } else if (warp == 3) {
       // ===================== ones column (kOnes): V[:, d] = 1 so that O[:, d] accumulates the row sums ============
       if constexpr (kOnes) {
         const uint32_t col_byte = (uint32_t)d * 2u;
@@ -952,7 +958,7 @@ ext_attn_q4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       }
     }
   } else {
-    warpgroup_reg_inc<104>();
+    warpgroup_reg_inc<(kTiles == 2 ? 104 : 96)>();
     // ===================== softmax streams: (tile X, key half H, lane quadrant) =====================
     const int sid = warp - 4;
     const int X = sid >> 3;
@@ -1097,18 +1103,19 @@ ext_attn_q4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   __syncthreads();
   if (warp == 1) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
-template <int kPoly16, bool kOnes>
+template <int kPoly16, bool kOnes, int kTiles>
 int launch_q4(const void* q, const void* k, const void* v, long long q_tok_stride, long long kv_tok_stride,
               int q_samples_total, int kv_samples_total, const AttnTable& tab, int n_out, int S, int heads, int d,
               float scale, void* out, int q_row0, int q_nrows, cudaStream_t stream) {
   constexpr int kBlockN = 128;
-  constexpr int kQBytes = 2 * kBlockM * 128, kStageBytes = 2 * kBlockN * 128;
+  constexpr int kQBytes = kTiles * kBlockM * 128, kStageBytes = 2 * kBlockN * 128;
   int stages = (227 * 1024 - 1024 - (int)sizeof(AttnCtl4) - 64 - kQBytes) / kStageBytes;
   if (stages > kPPStagesMax) stages = kPPStagesMax;
+  if (kTiles == 1) stages = 2;                           // two CTAs per SM: 1 KB + 16 KB Q + 2 x 32 KB ring + control each
   const size_t smem_bytes = 1024 + kQBytes + (size_t)stages * kStageBytes + sizeof(AttnCtl4);
   CUtensorMap map_q, map_k, map_v;
   auto make = [&](CUtensorMap* m, const void* base, long long tok_stride, int samples, int box_rows) -> int {
@@ -1126,17 +1133,17 @@ int launch_q4(const void* q, const void* k, const void* v, long long q_tok_strid
   AttnParams prm;
   prm.S = S; prm.heads = heads; prm.d = d; prm.n_out = n_out;
   prm.q_row0 = q_row0; prm.q_row_end = (q_row0 + q_nrows < S) ? q_row0 + q_nrows : S; prm.out_rows = q_nrows;
-  prm.tiles_m = (prm.q_row_end - q_row0 + 2 * kBlockM - 1) / (2 * kBlockM);
+  prm.tiles_m = (prm.q_row_end - q_row0 + kTiles * kBlockM - 1) / (kTiles * kBlockM);
   prm.handoff = 0;
   prm.stages = stages;
   prm.scale_log2 = scale * 1.4426950408889634f;
   prm.out_tok_stride = (long long)heads * d;
-  auto kern = ext_attn_q4_kernel<kPoly16, kOnes>;
+  auto kern = ext_attn_q4_kernel<kPoly16, kOnes, kTiles>;
   if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes),
                  "tf_ext_attn smem attribute"))
     return TF_ERR_CUDA;
   const long long grid = (long long)n_out * heads * prm.tiles_m;
-  kern<<<(unsigned)grid, 640, smem_bytes, stream>>>(map_q, map_k, map_v, tab, prm, static_cast<__half*>(out));
+  kern<<<(unsigned)grid, kTiles == 2 ? 640 : 384, smem_bytes, stream>>>(map_q, map_k, map_v, tab, prm, static_cast<__half*>(out));
   return check_cuda(cudaGetLastError(), "tf_ext_attn launch");
 }
 
@@ -2254,14 +2261,21 @@ int launch_ext_attn(const void* q, const void* k, const void* v, long long q_tok
   if (d <= 64 && rows > 128 && !force_v1) {
     const bool can_ones = (d % 16) != 0;            // a zero-padded column inside the P V MMA's N exists
     const bool ones = can_ones && (env_ones ? atoi(env_ones) != 0 : kDefaultOnes);
+    static const char* env_tiles = getenv("TF_EXT_ATTN_TILES");
+    const bool one_tile = env_tiles ? atoi(env_tiles) == 1 : kDefaultOneTile;
     const bool pp = mode && mode[0] == 'p';         // TF_EXT_ATTN_MODE=pp: the ping-pong kernel (one stream per query tile)
     const int poly = env_poly ? atoi(env_poly) : (pp ? 0 : (ones ? kDefaultPolyOnes : kDefaultPoly));
 #define TF_PP(P, O)                                                                                              \
     return launch_pp<128, P, O>(q, k, v, q_tok_stride, kv_tok_stride, q_samples_total, kv_samples_total, tab, n_out, \
                                 S, heads, d, scale, out, q_row0, q_nrows, stream)
 #define TF_Q4(P, O)                                                                                              \
-    return launch_q4<P, O>(q, k, v, q_tok_stride, kv_tok_stride, q_samples_total, kv_samples_total, tab, n_out, S,  \
-                           heads, d, scale, out, q_row0, q_nrows, stream)
+    do {                                                                                                         \
+      if (one_tile)                                                                                              \
+        return launch_q4<P, O, 1>(q, k, v, q_tok_stride, kv_tok_stride, q_samples_total, kv_samples_total, tab, n_out, S, \
+                                  heads, d, scale, out, q_row0, q_nrows, stream);                              \
+      return launch_q4<P, O, 2>(q, k, v, q_tok_stride, kv_tok_stride, q_samples_total, kv_samples_total, tab, n_out, S,   \
+                                heads, d, scale, out, q_row0, q_nrows, stream);                                \
+    } while (0)
     if (pp) {
       if (ones) { if (poly == 0) TF_PP(0, true); TF_PP(4, true); }
       if (poly == 0) TF_PP(0, false);

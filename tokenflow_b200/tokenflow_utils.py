@@ -33,7 +33,7 @@ from .util import isinstance_str, batch_cosine_sim  # noqa: F401  (re-exported l
 
 __all__ = [
     "register_pivotal", "register_batch_idx", "register_frame_table", "register_shard", "register_fused",
-    "PivotalShard",
+    "PivotalShard", "set_strict_dtype",
     "register_time", "load_source_latents_t",
     "register_conv_injection", "register_extended_attention_pnp", "register_extended_attention",
     "make_tokenflow_attention_block", "set_tokenflow", "isinstance_str", "batch_cosine_sim",
@@ -60,9 +60,19 @@ def _install_ops_for_testing(ops) -> None:
     _OPS = ops
 
 
+_STRICT_DTYPE = None
+
+
+def set_strict_dtype(flag) -> None:
+    """True: the blended frame-pass output is fp32 like the reference's promoted dtype (:385-388); False: fp16
+    (half the HBM write, same values to fp16 rounding); None: follow TOKENFLOW_B200_STRICT_DTYPE (default off)."""
+    global _STRICT_DTYPE
+    _STRICT_DTYPE = None if flag is None else bool(flag)
+
+
 def _strict_dtype() -> bool:
-    """TOKENFLOW_B200_STRICT_DTYPE=1: blended frame-pass output in fp32 like the reference's
-    promoted dtype (:385-388); default fp16 (half the HBM write, same values to fp16 rounding)."""
+    if _STRICT_DTYPE is not None:
+        return _STRICT_DTYPE
     return os.environ.get("TOKENFLOW_B200_STRICT_DTYPE", "0") == "1"
 
 
