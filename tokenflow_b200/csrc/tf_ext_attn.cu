@@ -29,6 +29,7 @@
 // Roofline: tensor-bound, 4*S_q*S_kv*d flops per (sample, head); HBM traffic is q,k,v,out once
 // (K/V tiles re-read by the other query tiles hit L2).
 #include <cstdlib>
+#include <type_traits>
 
 #include "tf_common.cuh"
 #include "tf_kernels.h"
@@ -977,11 +978,16 @@ ext_attn_q4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       if (++slab_tile == tiles_per_slab) slab_tile = 0;
       mbar_wait(&ctl->s_full[X], (uint32_t)(t & 1));
       tc_fence_after_sync();
+      // The tile body exists twice (generic lambda): full tiles never execute the 128 compare/select instructions of
+      // the key mask (written as a plain `if (valid < 64)` the compiler drops the outer test — the inner per-column
+      // tests imply it — and runs the selects on every tile: 128 ALU-pipe instructions per thread and tile).
+      auto tile_body = [&](auto masked_tag) {
+      constexpr bool kMasked = decltype(masked_tag)::value;
       uint32_t v[2][32];
       tmem_ld32(s_addr, v[0]);
       tmem_ld32(s_addr + 32, v[1]);
       tmem_wait_ld();
-      if (valid < 64) {
+      if constexpr (kMasked) {                     // ragged last key tile of a slab: -inf for the padding keys
 #pragma unroll
         for (int c = 0; c < 2; ++c)
 #pragma unroll
@@ -1048,6 +1054,8 @@ ext_attn_q4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       tc_fence_before_sync();
       __syncwarp();
       if (lane_id() == 0) mbar_arrive(&ctl->p_full[X][H]);
+      };
+      if (valid < 64) tile_body(std::true_type{}); else tile_body(std::false_type{});
     }
     // ---- final merge of the two key halves of a row, O / L -> fp16 ----
     mbar_wait(&ctl->pv_done[X][H][(T - 1) & 1], (uint32_t)(((T - 1) >> 1) & 1));
@@ -1701,11 +1709,16 @@ ext_attn_q4d_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       if (++slab_tile == tiles_per_slab) slab_tile = 0;
       mbar_wait(&ctl->s_full[X], (uint32_t)(t & 1));
       tc_fence_after_sync();
+      // The tile body exists twice (generic lambda): full tiles never execute the 128 compare/select instructions of
+      // the key mask (written as a plain `if (valid < 64)` the compiler drops the outer test — the inner per-column
+      // tests imply it — and runs the selects on every tile: 128 ALU-pipe instructions per thread and tile).
+      auto tile_body = [&](auto masked_tag) {
+      constexpr bool kMasked = decltype(masked_tag)::value;
       uint32_t v[2][32];
       tmem_ld32(s_addr, v[0]);
       tmem_ld32(s_addr + 32, v[1]);
       tmem_wait_ld();
-      if (valid < 64) {
+      if constexpr (kMasked) {                     // ragged last key tile of a slab: -inf for the padding keys
 #pragma unroll
         for (int c = 0; c < 2; ++c)
 #pragma unroll
@@ -1768,6 +1781,8 @@ ext_attn_q4d_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       tc_fence_before_sync();
       __syncwarp();
       if (lane_id() == 0) mbar_arrive(&ctl->p_full[X]);
+      };
+      if (valid < 64) tile_body(std::true_type{}); else tile_body(std::false_type{});
     }
     // ---- final: [O_u | O_c] / L -> fp16, the two halves write alternate 16-column chunks ----
     mbar_wait(&ctl->pv_done[X][(T - 1) & 1], (uint32_t)(((T - 1) >> 1) & 1));
@@ -2039,11 +2054,16 @@ ext_attn_h2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       const uint32_t s_addr = tmem_base + t_lane + (uint32_t)(b * kBlockN + H * 64);
       mbar_wait(&ctl->s_full[b], par);
       tc_fence_after_sync();
+      // The tile body exists twice (generic lambda): full tiles never execute the 128 compare/select instructions of
+      // the key mask (written as a plain `if (valid < 64)` the compiler drops the outer test — the inner per-column
+      // tests imply it — and runs the selects on every tile: 128 ALU-pipe instructions per thread and tile).
+      auto tile_body = [&](auto masked_tag) {
+      constexpr bool kMasked = decltype(masked_tag)::value;
       uint32_t v[2][32];
       tmem_ld32(s_addr, v[0]);
       tmem_ld32(s_addr + 32, v[1]);
       tmem_wait_ld();
-      if (valid < 64) {
+      if constexpr (kMasked) {                     // ragged last key tile of a slab: -inf for the padding keys
 #pragma unroll
         for (int c = 0; c < 2; ++c)
 #pragma unroll
@@ -2109,6 +2129,8 @@ ext_attn_h2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       tc_fence_before_sync();
       __syncwarp();
       if (lane_id() == 0) mbar_arrive(&ctl->p_full[b][H]);
+      };
+      if (valid < 64) tile_body(std::true_type{}); else tile_body(std::false_type{});
     }
     // ---- final merge of the two key halves of a row ----
     mbar_wait(&ctl->pv_done[H][(T - 1) & 1], (uint32_t)(((T - 1) >> 1) & 1));

@@ -1,6 +1,7 @@
 #!/bin/bash
 # 1-GPU box: full GPU test tier, paired-kernel sweep, one-tile (two CTAs per SM) sweep, d=80 two-half kernel sweep
 mkdir -p gpurun_out
+timeout 300 python __graft_entry__.py smoke 2>&1 | tail -3
 timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/r2_pytest6.log 2>&1; echo "pytest rc=$?"; tail -25 gpurun_out/r2_pytest6.log | cut -c1-300
 rm -f gpurun_out/r2_attn_pairs.jsonl
 ab() { tag=$1; shift; env "$@" timeout 200 python tools/attn_bench.py --tag "$tag" $EXTRA 2>&1 | tail -1 | cut -c1-220 | tee -a gpurun_out/r2_attn_pairs.jsonl; }
