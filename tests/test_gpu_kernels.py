@@ -355,7 +355,12 @@ def test_ext_attn_table_matches_whole_pass(ops):
                 out = ops.ext_attn_table(q_src, padded[1], padded[2], sh.attention_table(inject), heads, d ** -0.5)
                 for j, i in enumerate(sh.slots):
                     if i < 3 * K:
-                        assert torch.equal(out[j], whole[i]), (G, r, j)
+                        if inject and i >= K:
+                            # the whole pass pairs the uncond / cond sample of a keyframe (shared q, k: one kernel computes
+                            # their probabilities once); a rank that holds only one of the two runs the per-sample kernel
+                            assert (out[j].float() - whole[i].float()).abs().max().item() < 1e-3, (G, r, j)
+                        else:
+                            assert torch.equal(out[j], whole[i]), (G, r, j)
 
 
 def test_nn_field_sd21_token_counts(ops):

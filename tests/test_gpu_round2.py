@@ -415,9 +415,8 @@ def test_sharded_cuda_path_in_one_process(world, token_split):
     import threading
     steps, n_frames, batch = 4, 8, 2
 
-    def edit(world_size, rank, comm, out):
+    def edit(world_size, rank, comm, out, unet):
         try:
-            unet = sd_unet.build_unet("tiny", seed=1, device="cuda", dtype=torch.float16)
             cfg = {"n_frames": n_frames, "batch_size": batch, "n_timesteps": steps, "guidance_scale": 7.5, "mode": "pnp",
                    "pnp_attn_t": 0.5, "pnp_f_t": 0.8, "fused_pass": True, "cuda_graph": False, "keyframe_seed": 1,
                    "token_split": token_split}
@@ -436,13 +435,16 @@ def test_sharded_cuda_path_in_one_process(world, token_split):
 
     tfu._install_ops_for_testing(None)
     tfu._ops()                                              # one op object for all threads
+    # the models are built one after the other in this thread: build_unet seeds the process-global CPU generator,
+    # which rank threads would race for (separate processes each have their own)
+    unets = [sd_unet.build_unet("tiny", seed=1, device="cuda", dtype=torch.float16) for _ in range(world + 1)]
     ref = {}
-    edit(1, 0, None, ref)
+    edit(1, 0, None, ref, unets[world])
     assert not isinstance(ref[0], BaseException), ref[0]
     want, kf_want = ref[0]
     tw = _ThreadWorld(world)
     res = {}
-    threads = [threading.Thread(target=edit, args=(world, r, tw.rank(r), res)) for r in range(world)]
+    threads = [threading.Thread(target=edit, args=(world, r, tw.rank(r), res, unets[r])) for r in range(world)]
     for t in threads:
         t.start()
     for t in threads:

@@ -350,8 +350,9 @@ ext_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 // ================================================================================================
 constexpr int kPPStagesMax = 12;
 constexpr bool kDefaultOnes = true;        // measured choices (profiles/r02_ext_attn_variants.md)
-constexpr int kDefaultPolyOnes = 3, kDefaultPoly = 4, kDefaultPolyPair = 3, kDefaultPolyH2 = 3;
+constexpr int kDefaultPolyOnes = 3, kDefaultPoly = 4, kDefaultPolyPair = 4, kDefaultPolyH2 = 3;
 constexpr bool kDefaultOneTile = false;
+constexpr int kDefaultTurn = 0;
 struct AttnCtl2 {
   uint64_t q_full;
   uint64_t kv_full[kPPStagesMax];
@@ -779,6 +780,7 @@ struct AttnCtl4 {
   uint64_t p_full[2][2];       // [tile X][half]
   uint64_t pv_done[2][2][2];   // [tile X][half][t & 1]
   uint64_t fin[2];             // [tile X]: the R half published its (max, sum) for the final merge
+  uint64_t turn[2];            // [tile X]: all 8 softmax warps of tile X finished the exp2 phase of their current tile
   float2 ml_r[2][128];         // [tile X][row]: running max and row sum of the R half
   uint32_t tmem_base;
 };
@@ -841,6 +843,7 @@ ext_attn_q4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     for (int x = 0; x < 2; ++x) {
       mbar_init(&ctl->s_full[x], 1);
       mbar_init(&ctl->fin[x], 4);
+      mbar_init(&ctl->turn[x], 8);
       for (int hh = 0; hh < 2; ++hh) {
         mbar_init(&ctl->p_full[x][hh], 4);
         mbar_init(&ctl->pv_done[x][hh][0], 1);
@@ -856,7 +859,7 @@ ext_attn_q4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
 
   if (warp < 4) {
-    warpgroup_reg_dec<(kTiles == 2 ? 64 : 56)>();
+    warpgroup_reg_dec<(kTiles == 2 ? 64 : 40)>();   // per-CTA pool: 128*40 + 256*96 <= 384*80
     if (warp == 0) {
       // ===================== TMA producer =====================
       if (elect_one()) {
@@ -1028,6 +1031,14 @@ ext_attn_q4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           tmem_wait_st();
         }
       }
+      // exp2 phases of the two query tiles take turns (prm.handoff): tile B's phase of key tile t starts when tile A's
+      // is done and tile A's phase of t+1 when tile B's of t is done, so that one tile's score round trip (P V, the
+      // next Q K^T, commit, wake-up: ~900 cycles) runs under the other tile's exp2 phase instead of both tiles
+      // computing together and then waiting together (profiles/r02_ext_attn_variants.md)
+      if (kTiles == 2 && prm.handoff) {
+        if (X == 0) { if (t > 0) mbar_wait(&ctl->turn[1], (uint32_t)((t - 1) & 1)); }
+        else mbar_wait(&ctl->turn[0], (uint32_t)(t & 1));
+      }
       const float neg_m = -m_run;
       float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -1050,6 +1061,10 @@ ext_attn_q4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         if (c > 0) tmem_st16(s_addr + 16 * (c - 1), pk);
       }
       if (!kOnes) l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      if (kTiles == 2 && prm.handoff) {            // exp2 instructions issued: the other tile may start its phase
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(&ctl->turn[X]);
+      }
       tmem_wait_st();
       tc_fence_before_sync();
       __syncwarp();
@@ -1142,7 +1157,8 @@ int launch_q4(const void* q, const void* k, const void* v, long long q_tok_strid
   prm.S = S; prm.heads = heads; prm.d = d; prm.n_out = n_out;
   prm.q_row0 = q_row0; prm.q_row_end = (q_row0 + q_nrows < S) ? q_row0 + q_nrows : S; prm.out_rows = q_nrows;
   prm.tiles_m = (prm.q_row_end - q_row0 + kTiles * kBlockM - 1) / (kTiles * kBlockM);
-  prm.handoff = 0;
+  static const char* env_turn = getenv("TF_EXT_ATTN_TURN");
+  prm.handoff = env_turn ? atoi(env_turn) : kDefaultTurn;
   prm.stages = stages;
   prm.scale_log2 = scale * 1.4426950408889634f;
   prm.out_tok_stride = (long long)heads * d;

@@ -19,8 +19,14 @@ resid = torch.randn(3 * B, S, dim, device="cuda").half()
 kf_a, kf_b, w = [2] * B, [1] * B, blend_weights(B)
 norm = torch.nn.LayerNorm(dim).cuda().half()
 hid = torch.randn(B, S, dim, device="cuda").half()
+S2, dim2 = 1024, 640                                     # SD1.5 middle level (d = 80): the two-half kernel
+q2, k2, v2 = (torch.randn(3 * n, S2, dim2, device="cuda").half() for _ in range(3))
+hid_piv = torch.randn(3 * n, S, dim, device="cuda").half()
 for _ in range(3):
-    ops.ext_attn(q, k, v, heads, d ** -0.5, False)
+    ops.ext_attn(q, k, v, heads, d ** -0.5, False)       # quad-stream kernel, all 15 samples
+    ops.ext_attn(q, k, v, heads, d ** -0.5, True)        # PnP injection: paired kernel (uncond + cond) + source samples
+    ops.ext_attn(q2, k2, v2, heads, (dim2 // heads) ** -0.5, False)
+    ops.layernorm_rows(hid_piv, norm, n)
     ops.layernorm_unit_rows(hid, norm)
     xu, pu = ops.unit_rows(x), ops.unit_rows(piv)
     idx_a, idx_b = ops.nn_field(xu, pu, kf_a, kf_b)
