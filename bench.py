@@ -138,7 +138,7 @@ def dist_env():
 # our arm
 # ------------------------------------------------------------------------------------------------
 def build_editor(device, cfg_name="C2", world=1, rank=0, seed=1, channels_last=True, frames_per_pass=None, fused_pass=True,
-                 cuda_graph=True, hooks=None, unet=None, check_keyframes=False, comm=None):
+                 cuda_graph=True, hooks=None, unet=None, check_keyframes=False, comm=None, dual_stream=None):
     from tokenflow_b200 import sd_unet, tokenflow_utils as tfu
     from tokenflow_b200.editor import TokenFlowEditor, synthetic_inputs
     from tokenflow_b200.scheduler import DDIMScheduler
@@ -153,7 +153,7 @@ def build_editor(device, cfg_name="C2", world=1, rank=0, seed=1, channels_last=T
            "mode": c["mode"], "pnp_attn_t": 0.5, "pnp_f_t": 0.8, "start": 0.9,
            "frames_per_pass": frames_per_pass if frames_per_pass else c["n_frames"],
            "fused_pass": bool(fused_pass), "cuda_graph": bool(cuda_graph), "keyframe_seed": seed,
-           "check_keyframes": bool(check_keyframes)}
+           "check_keyframes": bool(check_keyframes), "dual_stream": dual_stream}
     x, text, pnp, src = synthetic_inputs(c["n_frames"], c["latent"], unet.config.cross_attention_dim, c["n_timesteps"],
                                          seed=seed, device=device, dtype=torch.float16)
     ed = TokenFlowEditor(unet, DDIMScheduler(), hooks or tfu, cfg, text, pnp, source_latents=lambda t: src[t],
@@ -210,7 +210,8 @@ def run_verify(args, device, world, rank, ed, x0, cfg_name, steps=2):
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(mism, op=dist.ReduceOp.SUM)
     # graphs vs eager on the SAME world size (must be identical: same kernels, same order)
-    eager, xe, _ = build_editor(device, cfg_name, world, rank, cuda_graph=False, unet=ed.unet, comm=ed.comm)
+    eager, xe, _ = build_editor(device, cfg_name, world, rank, cuda_graph=False, unet=ed.unet, comm=ed.comm,
+                                dual_stream=ed.config.get("dual_stream"))
     for i in range(steps):
         xe = eager.step_index(xe, i)
     ed.init_method()
@@ -272,7 +273,8 @@ def run_ours(args):
     torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)
     ed, x0, src = build_editor(device, cfg_name, world, rank, channels_last=not args.no_channels_last,
                                frames_per_pass=args.frames_per_pass, fused_pass=bool(args.fused_pass),
-                               cuda_graph=bool(args.graph), comm=comm)
+                               cuda_graph=bool(args.graph), comm=comm,
+                               dual_stream=None if args.dual_stream < 0 else bool(args.dual_stream))
     timesteps = list(ed._t_host)
     n_sched = len(timesteps)
 
@@ -427,7 +429,11 @@ def run_ours(args):
                    "parallelism": f"frames sharded over {world} GPU(s)" if world > 1 else "single GPU",
                    "frames_per_pass": (N // world) if (world > 1 or args.fused_pass) else args.frames_per_pass,
                    "unet_calls_per_step": 1 if args.fused_pass else (2 if world > 1 else 1 + -(-N // (args.frames_per_pass or N))),
-                   "cuda_graph": bool(args.graph), "collectives": ("tf_allgather (C ABI, NCCL)" if comm is not None else
+                   "cuda_graph": bool(args.graph),
+                   "schedule": ("dual-stream: pivotal pass on a side stream under the frame pass, per-block events"
+                                if (ed.config.get("dual_stream") if ed.config.get("dual_stream") is not None else world > 1)
+                                else "fused: pivotal + frame samples in one UNet call"),
+                   "collectives": ("tf_allgather (C ABI, NCCL)" if comm is not None else
                                                                    ("torch.distributed" if world > 1 else None)),
                    "l2": "inputs > L2: every step streams ~10 GB of activations through the UNet (no flush needed)"},
         "e2e": {"value": fps_e2e, "unit": "frames/s", "ms_per_step": ms_step_e2e,
@@ -647,6 +653,9 @@ def main():
     ap.add_argument("--verify", action="store_true",
                     help="before timing: 2 steps of the measured path vs the 1-rank eager path (max |diff|, NN-index mismatches)")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the fused step as a CUDA graph (default); 0: eager")
+    ap.add_argument("--dual-stream", type=int, default=-1,
+                    help="1: pivotal pass on a side stream concurrent with the frame pass; 0: one fused UNet call; "
+                         "-1 (default): dual-stream when sharded over several GPUs, fused on one GPU")
     ap.add_argument("--no-kernel-events", action="store_true", help="capture / run without per-launch timing events")
     ap.add_argument("--torch-collectives", action="store_true", help="all-gathers through torch.distributed instead of the C ABI")
     ap.add_argument("--no-cpu-baseline", action="store_true")

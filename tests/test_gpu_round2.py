@@ -361,6 +361,26 @@ def test_cuda_graph_step_identical_to_eager(mode, steps):
     assert ed_t.graph_launches_per_step() >= 16 * 4
 
 
+@pytest.mark.parametrize("graph", [False, True])
+def test_dual_stream_step_matches_fused_step(graph):
+    """The dual-stream schedule (pivotal pass on a side stream, frame pass on the current stream, per-block events)
+    computes the same edit as the fused single call (body GEMMs / convs see other batch sizes: fp16 accumulation-order
+    noise only), and its CUDA-graph replay equals its eager run bit for bit."""
+    def run(dual, use_graph):
+        ed, x = _editor("pnp", 5, graph=use_graph)
+        ed.config["dual_stream"] = dual
+        out = ed.sample_loop(x.clone())
+        return out, ed.keyframe_log
+    want, kf_w = run(False, False)
+    got, kf_g = run(True, graph)
+    assert kf_g == kf_w and torch.isfinite(got).all()
+    rel = ((got.float() - want.float()).norm() / want.float().norm()).item()
+    assert rel < 2e-2, rel
+    if graph:
+        eager, _ = run(True, False)
+        assert torch.equal(got, eager)
+
+
 def test_edit_with_strict_dtype(monkeypatch):
     """TOKENFLOW_B200_STRICT_DTYPE=1: the blended frame-pass output is the reference's promoted fp32; the edit
     still matches the reference GPU arithmetic."""
@@ -397,6 +417,7 @@ class _ThreadWorld:
         def all_gather(self, t):
             P = self.parent
             P.slots[self.rank] = t.contiguous()
+            torch.cuda.current_stream().synchronize()      # rank threads may run on different (side) streams
             P.barrier.wait()
             out = torch.cat(list(P.slots))
             P.barrier.wait()
@@ -406,9 +427,9 @@ class _ThreadWorld:
         return _ThreadWorld._Rank(self, r)
 
 
-@pytest.mark.parametrize("token_split", [True, False])
+@pytest.mark.parametrize("token_split,dual", [(True, True), (True, False), (False, False)])
 @pytest.mark.parametrize("world", [2, 4])
-def test_sharded_cuda_path_in_one_process(world, token_split):
+def test_sharded_cuda_path_in_one_process(world, token_split, dual):
     """The multi-GPU code path of the hooks on the CUDA kernels (packed q|k|v|unit gather, query-row split of the
     extended attention with the paired kernel, output re-assembly, sharded conv injection) with `world` rank threads
     on one GPU == the single-rank edit."""
@@ -419,7 +440,7 @@ def test_sharded_cuda_path_in_one_process(world, token_split):
         try:
             cfg = {"n_frames": n_frames, "batch_size": batch, "n_timesteps": steps, "guidance_scale": 7.5, "mode": "pnp",
                    "pnp_attn_t": 0.5, "pnp_f_t": 0.8, "fused_pass": True, "cuda_graph": False, "keyframe_seed": 1,
-                   "token_split": token_split}
+                   "token_split": token_split, "dual_stream": dual and world_size > 1}
             x, text, pnp, src = synthetic_inputs(n_frames, 16, unet.config.cross_attention_dim, steps, seed=1,
                                                  device="cuda", dtype=torch.float16, ctx_len=7)
             ed = TokenFlowEditor(unet, DDIMScheduler(), tfu, cfg, text, pnp, source_latents=lambda t: src[t],

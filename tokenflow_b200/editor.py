@@ -70,6 +70,7 @@ class TokenFlowEditor(nn.Module):
         self._g_static = None
         self._text_cache = {}
         self._shard_cache = {}
+        self._side_stream = None
 
     # ------------------------------------------------------------------------------------
     def init_method(self):
@@ -318,6 +319,67 @@ class TokenFlowEditor(nn.Module):
         dist.all_gather_into_tensor(out, x_local, group=self.group)
         return out
 
+    def _dual_compute(self, x, src_all, piv_idx, t_dev, t_int, coef, slots, shard):
+        """The same step as `_fused_compute` as TWO UNet calls on two CUDA streams: the pivotal samples (few, and all
+        the collectives when sharded) on a side stream, this rank's frames on the current stream; each TokenFlow block
+        of the frame call waits for the event its pivotal counterpart recorded (`register_dual_stream`).  The pivotal
+        chain — latency-bound small kernels plus the all-gathers — then runs under the frame chain's compute."""
+        h, G, r = self.hooks, self.world_size, self.rank
+        N = x.shape[0]
+        per = N // G
+        lo = r * per
+        main = torch.cuda.current_stream()
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=self.device)
+        side = self._side_stream
+        piv_lat = torch.cat([src_all, x]).index_select(0, piv_idx)
+        text = self._fused_text(slots, per)
+        n_piv = len(slots)
+        piv_emb, frame_emb = text[:n_piv], text[n_piv:]
+        xs, srcs = x[lo:lo + per], src_all[lo:lo + per]
+        frame_in = torch.cat([srcs, xs, xs])
+        h.register_time(self, t_int)
+        h.register_fused(self, 0)
+        h.register_dual_stream(self, True)
+        try:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):                    # ---- pivotal chain
+                h.register_pivotal(self, True)
+                h.register_shard(self, shard)
+                self.unet(piv_lat, t_dev, encoder_hidden_states=piv_emb)
+            h.register_pivotal(self, False)                  # ---- frame chain
+            h.register_shard(self, None)
+            h.register_frame_table(self, *self.frame_table(list(range(lo, lo + per))))
+            noise_pred = self.unet(frame_in, t_dev, encoder_hidden_states=frame_emb)['sample']
+            main.wait_stream(side)                           # join (piv_lat and the caches stay referenced until here)
+        finally:
+            h.register_dual_stream(self, False)
+            h.register_shard(self, None)
+        del piv_lat
+        _, npu, npc = noise_pred.chunk(3)
+        ops = self._cuda_ops()
+        if ops is not None and coef is not None and npu.dtype == torch.float16 and xs.dtype == torch.float16:
+            x_local = ops.cfg_ddim(npu, npc, xs, coef, self.config["guidance_scale"])
+        else:
+            noise_pred = npu + self.config["guidance_scale"] * (npc - npu)
+            x_local = self.scheduler.step(noise_pred, t_int, xs)['prev_sample'].contiguous()
+        if G == 1:
+            return x_local
+        if self.comm is not None and x_local.is_cuda:
+            return self.comm.all_gather(x_local)
+        import torch.distributed as dist
+        out = torch.empty_like(x)
+        dist.all_gather_into_tensor(out, x_local, group=self.group)
+        return out
+
+    def _step_compute(self, *a):
+        dual = self.config.get("dual_stream", None)
+        if dual is None:
+            dual = self.world_size > 1                       # default: on when sharded (hides the collectives)
+        if dual and self.device.type == "cuda":
+            return self._dual_compute(*a)
+        return self._fused_compute(*a)
+
     def _cuda_ops(self):
         """The CUDA op object if the hooks run on it (None under the oracle test seam / on CPU)."""
         if self.device.type != "cuda":
@@ -360,7 +422,7 @@ class TokenFlowEditor(nn.Module):
         if self.config.get("cuda_graph", False) and self.device.type == "cuda" and coef is not None:
             return self._graph_replay(x, src_all, idx_host, t_int, i, slots, shard)
         piv_idx = idx_host.to(x.device, non_blocking=True) if x.is_cuda else idx_host
-        return self._fused_compute(x, src_all, piv_idx, t_dev, t_int, coef, slots, shard)
+        return self._step_compute(x, src_all, piv_idx, t_dev, t_int, coef, slots, shard)
 
     # ------------------------------------------------------------------------------------
     # CUDA graphs: the fused step's shape is static, so it is captured once per injection
@@ -395,7 +457,7 @@ class TokenFlowEditor(nn.Module):
 
     def _capture(self, st, t_int, slots, shard):
         ops = self._cuda_ops()
-        run = lambda: self._fused_compute(st["x"], st["src"], st["idx"], st["t"], t_int, st["coef"], slots, shard)
+        run = lambda: self._step_compute(st["x"], st["src"], st["idx"], st["t"], t_int, st["coef"], slots, shard)
         # warm-up on a side stream (cuDNN autotuning, lazy initialisation, allocator growth) — not captured
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())

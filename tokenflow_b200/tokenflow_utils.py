@@ -33,7 +33,7 @@ from .util import isinstance_str, batch_cosine_sim  # noqa: F401  (re-exported l
 
 __all__ = [
     "register_pivotal", "register_batch_idx", "register_frame_table", "register_shard", "register_fused",
-    "PivotalShard", "set_strict_dtype",
+    "PivotalShard", "set_strict_dtype", "register_dual_stream",
     "register_time", "load_source_latents_t",
     "register_conv_injection", "register_extended_attention_pnp", "register_extended_attention",
     "make_tokenflow_attention_block", "set_tokenflow", "isinstance_str", "batch_cosine_sim",
@@ -225,6 +225,17 @@ def register_fused(diffusion_model, n_pivotal: int):
     res = _conv_injection_site(diffusion_model)
     if res is not None:
         res._tf_fused = int(n_pivotal)
+
+
+def register_dual_stream(diffusion_model, enabled: bool):
+    """Dual-stream schedule: the pivotal pass and the frame pass of a step are enqueued on two CUDA streams; every
+    TokenFlow block records an event when its keyframe caches are filled (pivotal pass) and the frame pass's block
+    waits for it before it reads them.  The pivotal chain (few samples, all the collectives) then runs under the
+    frame chain's compute instead of in front of it."""
+    for module in _transformer_blocks(diffusion_model):
+        module._tf_dual = bool(enabled)
+        if not enabled:
+            module._tf_ev_unit = module._tf_ev_out = None
 
 
 def register_shard(diffusion_model, shard: Optional[PivotalShard]):
@@ -565,6 +576,7 @@ def make_tokenflow_attention_block(block_class: Type[torch.nn.Module]) -> Type[t
                     self.attn_output = self.attn1(norm_hidden_states, **cross_attention_kwargs)
                 full = self.attn1.__dict__.pop("_tf_attn_full", None)         # token-split closure: already complete
                 self.kf_attn_output = full if full is not None else shard.all_gather(self.attn_output)[:3 * shard.K]
+                self._tf_record_ready()
             else:
                 n_frames = batch_size // 3
                 if fused_ln:
@@ -582,7 +594,16 @@ def make_tokenflow_attention_block(block_class: Type[torch.nn.Module]) -> Type[t
                     encoder_hidden_states=encoder_hidden_states if self.only_cross_attention else None,
                     **cross_attention_kwargs)
                 self.kf_attn_output = self.attn_output                                   # :360
+                self._tf_record_ready()
             return self.attn_output + hidden_states                                      # :397
+
+        def _tf_record_ready(self):
+            """Dual-stream schedule: mark the point on the pivotal pass's stream where this block's keyframe caches
+            (pivot unit rows, extended-attention output) are complete."""
+            if getattr(self, "_tf_dual", False) and self.kf_attn_output.is_cuda:
+                ev = torch.cuda.Event()
+                ev.record()
+                self._tf_ev_unit = self._tf_ev_out = ev
 
         def _tf_frames(self, hidden_states):
             """Self-attention stage of a frame pass: NN field + propagation (reference :329-348, :361-397)."""
@@ -599,6 +620,9 @@ def make_tokenflow_attention_block(block_class: Type[torch.nn.Module]) -> Type[t
             n_kf = kf.shape[0] // 3
             # norm1 of the source stream only — the other two thirds are never used in this branch (:335)
             x_unit = ops.layernorm_unit_rows(hidden_states[:n_frames], self.norm1)
+            ev = getattr(self, "_tf_ev_out", None) if getattr(self, "_tf_dual", False) else None
+            if ev is not None:                       # dual-stream schedule: the caches are filled on the other stream
+                torch.cuda.current_stream().wait_event(ev)
             idx_a, idx_b = ops.nn_field(x_unit, self._tf_pivot_unit, kf_a, kf_b)          # :335-343
             out_dtype = torch.float32 if (_strict_dtype() and idx_b is not None) else None
             self._tf_nn_idx = (idx_a, idx_b)
