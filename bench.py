@@ -431,7 +431,7 @@ def run_ours(args):
                    "unet_calls_per_step": 1 if args.fused_pass else (2 if world > 1 else 1 + -(-N // (args.frames_per_pass or N))),
                    "cuda_graph": bool(args.graph),
                    "schedule": ("dual-stream: pivotal pass on a side stream under the frame pass, per-block events"
-                                if (ed.config.get("dual_stream") if ed.config.get("dual_stream") is not None else world > 1)
+                                if ed.config.get("dual_stream")
                                 else "fused: pivotal + frame samples in one UNet call"),
                    "collectives": ("tf_allgather (C ABI, NCCL)" if comm is not None else
                                                                    ("torch.distributed" if world > 1 else None)),
@@ -654,8 +654,8 @@ def main():
                     help="before timing: 2 steps of the measured path vs the 1-rank eager path (max |diff|, NN-index mismatches)")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the fused step as a CUDA graph (default); 0: eager")
     ap.add_argument("--dual-stream", type=int, default=-1,
-                    help="1: pivotal pass on a side stream concurrent with the frame pass; 0: one fused UNet call; "
-                         "-1 (default): dual-stream when sharded over several GPUs, fused on one GPU")
+                    help="1: pivotal pass on a side stream concurrent with the frame pass (experimental: slower on one GPU, "
+                         "not validated with NCCL ranks); 0 / -1 (default): one fused UNet call per step")
     ap.add_argument("--no-kernel-events", action="store_true", help="capture / run without per-launch timing events")
     ap.add_argument("--torch-collectives", action="store_true", help="all-gathers through torch.distributed instead of the C ABI")
     ap.add_argument("--no-cpu-baseline", action="store_true")
