@@ -298,7 +298,9 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     launches0 = ops.launch_count()
-    if not args.graph:
+    if args.graph:
+        ed.mark_graph_replays()                          # kernel times below cover the timed replays only
+    else:
         ops.timing_summary()                             # drop the warm-up's events
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -310,11 +312,11 @@ def run_ours(args):
     ms_total = ev0.elapsed_time(ev1)
     launches = ops.launch_count() - launches0
     if args.graph:
-        # launches replayed from the graphs are not counted by the library's counter: count the graph's kernel nodes
-        kernel_times = ed.graph_kernel_times()            # last replay of each captured variant = one step
-        launches = sum(k_["launches"] for k_ in kernel_times.values()) * args.steps if kernel_times else \
+        # launches replayed from the graphs are not counted by the library's counter: count the graphs' kernel nodes
+        kernel_times, graph_steps = ed.graph_kernel_times(since_mark=True)     # replays of the timed region
+        launches = sum(k_["launches"] for k_ in kernel_times.values()) if kernel_times else \
             ed.graph_launches_per_step() * args.steps
-        per_step_div = 1.0
+        per_step_div = float(max(1, graph_steps)) if kernel_times else float(args.steps)
     else:
         kernel_times = ops.timing_summary()
         per_step_div = float(args.steps)

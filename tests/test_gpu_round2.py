@@ -354,7 +354,8 @@ def test_cuda_graph_step_identical_to_eager(mode, steps):
     ops_.enable_timing(True)
     try:
         ed_t.step_index(x.clone(), 0)
-        kt = ed_t.graph_kernel_times()
+        kt, n_steps = ed_t.graph_kernel_times()
+        assert n_steps == 1
     finally:
         ops_.enable_timing(False)
     assert kt["tf_ext_attn"]["launches"] == 16 and kt["tf_ext_attn"]["ms"] > 0

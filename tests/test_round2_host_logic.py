@@ -154,3 +154,22 @@ def test_bench_configs_match_baseline_json():
     assert bench.unet_levels("sd21", 96)[0] == (9216, 320, 5, 5)
     threads, probe = bench.pick_cpu_threads(3)
     assert threads == 3 and probe == {}
+
+
+def test_graph_event_aggregation_weights_variants_by_their_replays():
+    class Ev:
+        def __init__(self, t):
+            self.t = t
+
+        def elapsed_time(self, other):
+            return other.t - self.t
+    a = {"replays": 5, "mark": 2, "events": [("tf_ext_attn", 10.0, Ev(0.0), Ev(2.0)), ("tf_nn_field", 4.0, Ev(2.0), Ev(2.5))]}
+    b = {"replays": 1, "events": [("tf_ext_attn", 10.0, Ev(0.0), Ev(1.0))]}
+    c = {"replays": 3, "mark": 3, "events": [("tf_ext_attn", 10.0, Ev(0.0), Ev(9.0))]}      # not replayed since the mark
+    d = {"replays": 2, "events": None}                                                         # captured without timing
+    agg, steps = TokenFlowEditor.aggregate_graph_events([a, b, c, d], since_mark=True)
+    assert steps == 4
+    assert agg["tf_ext_attn"] == {"launches": 4, "ms": 3 * 2.0 + 1.0, "work": 40.0}
+    assert agg["tf_nn_field"] == {"launches": 3, "ms": 1.5, "work": 12.0}
+    agg_all, steps_all = TokenFlowEditor.aggregate_graph_events([a, b, c, d])
+    assert steps_all == 9 and agg_all["tf_ext_attn"]["launches"] == 9

@@ -491,20 +491,33 @@ class TokenFlowEditor(nn.Module):
         used = [e for e in self._graphs.values() if e["replays"]]
         return max((e["launches"] for e in used), default=0)
 
-    def graph_kernel_times(self):
-        """{kernel: {"launches", "ms", "work"}} of the LAST replay of every captured variant that has been
-        replayed (the event nodes are part of the graph; each replay overwrites their timestamps)."""
-        torch.cuda.synchronize()
-        agg = {}
+    def mark_graph_replays(self):
+        """Start of a measured region: `graph_kernel_times(since_mark=True)` then covers the replays after this call."""
         for entry in self._graphs.values():
-            if not entry["replays"] or not entry["events"]:
+            entry["mark"] = entry["replays"]
+
+    @staticmethod
+    def aggregate_graph_events(entries, since_mark=False):
+        """{kernel: {"launches", "ms", "work"}} over the replays of the captured step graphs.  The event nodes are part
+        of a graph and every replay overwrites their timestamps, so what can be read is the LAST replay of each
+        variant; a variant that was replayed n times contributes n times its last replay.  Returns (totals, steps)."""
+        agg, steps = {}, 0
+        for entry in entries:
+            n = entry["replays"] - (entry.get("mark", 0) if since_mark else 0)
+            if n <= 0 or not entry.get("events"):
                 continue
+            steps += n
             for name, work, s_, e_ in entry["events"]:
                 a = agg.setdefault(name, {"launches": 0, "ms": 0.0, "work": 0.0})
-                a["launches"] += 1
-                a["ms"] += s_.elapsed_time(e_)
-                a["work"] += work
-        return agg
+                a["launches"] += n
+                a["ms"] += n * s_.elapsed_time(e_)
+                a["work"] += n * work
+        return agg, steps
+
+    def graph_kernel_times(self, since_mark=False):
+        """Per-kernel totals of the step graphs' per-launch event nodes (see `aggregate_graph_events`)."""
+        torch.cuda.synchronize()
+        return self.aggregate_graph_events(self._graphs.values(), since_mark)
 
     # ------------------------------------------------------------------------------------
     # host-buffer entry point (bench `e2e`): latents live in pinned host memory
