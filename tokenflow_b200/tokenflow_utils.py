@@ -432,7 +432,7 @@ def _sa_forward(attn, pnp: bool):
                 # sharded pivotal pass, query rows split over the ranks: ONE all-gather of [q | k | v | pivot unit rows]
                 # per sample, attention of all 3K samples for this rank's query rows, to_out on those rows, ONE
                 # all-gather of the result (the block picks the complete [3K, S, dim] output up from the closure)
-                q = torch.nn.functional.linear(x, attn.to_q.weight.to(torch.float16))
+                q = torch.nn.functional.linear(x, _fused_weight(attn, ("to_q",), torch.float16))
                 kv = torch.nn.functional.linear(x, _fused_weight(attn, ("to_k", "to_v"), torch.float16))
                 unit = attn.__dict__.pop("_tf_unit_local", None)
                 packed = shard.all_gather(torch.cat([q, kv] + ([unit] if unit is not None else []), dim=-1))
@@ -443,7 +443,7 @@ def _sa_forward(attn, pnp: bool):
             else:
                 # sharded pivotal pass: ONE all-gather of [k | v | pivot unit rows] along the sample axis
                 # (+ one of q only while PnP-injecting, when the source stream's q lives on another rank)
-                q = torch.nn.functional.linear(x, attn.to_q.weight.to(torch.float16))
+                q = torch.nn.functional.linear(x, _fused_weight(attn, ("to_q",), torch.float16))
                 kv = torch.nn.functional.linear(x, _fused_weight(attn, ("to_k", "to_v"), torch.float16))
                 unit = attn.__dict__.pop("_tf_unit_local", None)
                 packed = shard.all_gather(kv if unit is None else torch.cat([kv, unit], dim=-1))
