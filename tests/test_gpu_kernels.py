@@ -178,15 +178,31 @@ def test_nn_field_vs_oracle(ops, F, K, S, dim):
 
 
 def test_nn_field_matches_cublas_path(ops):
-    """The reference's own GPU arithmetic, executed here: fp16 cuBLAS GEMM (fp16 output) + argmax."""
+    """The reference's own GPU arithmetic, executed here: fp16 cuBLAS GEMM (fp16 output) + argmax.  Every index that
+    differs from cuBLAS's is classified against cuBLAS's OWN similarity values: both candidates must lie within 2 fp16
+    ulp of each other (each fp32-accumulated dot rounds to fp16 at most one ulp apart between two accumulation orders),
+    i.e. the row is a tie class whose winner the reference's GEMM does not pin either.  Counts are reported."""
     F, K, S, dim = 4, 2, 1024, 320
     x, piv = _video_like(F, K, S, dim, seed=9)
     xu, pu = ops.unit_rows(x), ops.unit_rows(piv)
     idx_a, idx_b = ops.nn_field(xu, pu, [1] * F, [0] * F)
-    ref_a = (xu.view(-1, dim) @ pu[1].T).argmax(-1).view(F, S)
-    ref_b = (xu.view(-1, dim) @ pu[0].T).argmax(-1).view(F, S)
-    mism = (idx_a.long() != ref_a).sum().item() + (idx_b.long() != ref_b).sum().item()
-    assert mism <= 0.005 * 2 * F * S, mism
+    total = mism = tie_class = 0
+    for idx, kf in ((idx_a, 1), (idx_b, 0)):
+        sim = xu.view(-1, dim) @ pu[kf].T                       # fp16 cuBLAS output, like util.py:68 under autocast
+        ref = sim.argmax(-1)
+        got = idx.long().view(-1)
+        bad = (got != ref).nonzero().squeeze(1)
+        total += got.numel()
+        mism += bad.numel()
+        if bad.numel():
+            gap = (sim[bad, ref[bad]].float() - sim[bad, got[bad]].float()).abs()
+            tie_class += int((gap <= 2.0 ** -10).sum())         # 2 ulp of fp16 values in [0.5, 1]
+    msg = f"NN field vs cuBLAS + argmax: {mism} of {total} indices differ, {tie_class} of them inside an fp16 tie class"
+    print(msg)
+    assert mism <= 0.005 * total, msg
+    # all of them tie classes — up to the few rows where cuBLAS itself may be more than one ulp off the exactly rounded
+    # dot (PyTorch lets it reduce split-K partial sums in fp16: allow_fp16_reduced_precision_reduction defaults to True)
+    assert mism - tie_class <= 5e-4 * total, msg
 
 
 def test_nn_field_first_index_on_exact_ties(ops):
