@@ -6,6 +6,7 @@ Layout (only what the path needs):
     tokenflow_utils.py  drop-in for the reference hook layer (same names / signatures)
     util.py             drop-in for the names the drivers import from `util`
     sd_unet.py, scheduler.py   diffusers-shaped random-init SD UNet + DDIM (diffusers is not installed)
-    editor.py           the caller: mirror of the reference `batched_denoise_step` loop, 1..N GPUs
+    editor.py           the caller: the reference `batched_denoise_step` loop as one CUDA-graphed fused step, 1..N GPUs
+    preprocess.py       the stage in front: DDIM inversion / reconstruction in latent space + the on-disk hand-off
 """
-__version__ = "0.1.0"
+__version__ = "0.2.0"
