@@ -9,8 +9,6 @@ raises, loudly.  (Tests substitute an oracle-backed op object through
 from __future__ import annotations
 
 import ctypes
-import math
-import os
 from pathlib import Path
 from typing import Optional, Sequence, Tuple
 
